@@ -1,0 +1,213 @@
+/* vlg.h -- C ABI of libvlg.so: the B200 (sm_100a) decode hot path of Video-LlamaGen.
+ *
+ * The reference (BinZhu-ece/Video-LlamaGen) is pure Python/PyTorch and has no FFI of
+ * its own; the boundary it offers is the Python surface of
+ *   autoregressive/models/gpt.py       (Transformer.setup_caches / forward, :318-385)
+ *   autoregressive/models/generate.py  (generate / prefill / decode_* / sample, :16-180)
+ *   tokenizer/tokenizer_image/vq_model.py (VectorQuantizer.forward / get_codebook_entry, :215-276)
+ * Each entry point below names the reference lines it replaces; INTEGRATION.md shows the
+ * ctypes binding a maintainer adds on the reference side.
+ *
+ * Conventions
+ *   - plain C types only; every pointer named *_dev is device memory owned by the caller
+ *     (a torch tensor kept alive by the Python side); *_host is host memory.
+ *   - every call returns VLG_OK or a negative vlg_status; vlg_last_error() gives the text.
+ *   - no call allocates or frees device memory except vlg_ctx_create/destroy (which own
+ *     only small descriptor/graph objects; the KV cache and activations live in the
+ *     caller-provided workspace) -- and no call synchronises the device unless its
+ *     comment says so.  `stream` is a cudaStream_t passed as void*.
+ *   - one host thread per context, one process per GPU (generate() in the reference is not
+ *     re-entrant either: it mutates model.causal_mask / KV caches, generate.py:154-165).
+ */
+#ifndef VLG_H_
+#define VLG_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VLG_ABI_VERSION 1
+
+typedef enum {
+  VLG_OK = 0,
+  VLG_ERR_ARG = -1,         /* bad argument / unsupported shape */
+  VLG_ERR_CUDA = -2,        /* a CUDA runtime/driver call failed */
+  VLG_ERR_UNSUPPORTED = -3, /* device is not sm_100 */
+  VLG_ERR_STATE = -4        /* call sequence violated (e.g. decode before prefill) */
+} vlg_status;
+
+typedef enum { VLG_F32 = 0, VLG_BF16 = 1 } vlg_dtype;
+typedef enum { VLG_C2I = 0, VLG_T2I = 1, VLG_T2V = 2 } vlg_model_type;
+
+int vlg_abi_version(void);
+const char* vlg_last_error(void);
+
+/* ------------------------------------------------------------------------------------------
+ * VQ tokenizer index search -- replaces VectorQuantizer.forward (vq_model.py:215-259, eval mode)
+ * and get_codebook_entry (vq_model.py:261-276).
+ * ------------------------------------------------------------------------------------------ */
+
+/* z_dev        fp32 [B, C, HW]  (the [B,C,H,W] activations the reference passes in, C = e_dim)
+ * codebook_dev fp32 [n_e, C]    raw embedding.weight (normalised inside when l2_norm != 0)
+ * idx_dev      int64 [B*HW]     argmin_j ( |z|^2 + |e_j|^2 - 2 z.e_j ), first index on ties
+ * zq_dev       fp32 [B, C, HW]  selected (normalised) codebook rows, channel-first; may be NULL
+ * scratch_dev  fp32 [n_e * (C+1)] work area for the normalised codebook and |e_j|^2          */
+int vlg_vq_argmin(const float* z_dev, const float* codebook_dev, int64_t* idx_dev, float* zq_dev,
+                  float* scratch_dev, int64_t B, int C, int64_t HW, int n_e, int l2_norm, void* stream);
+
+/* out_dev fp32: channel_first ? [B, C, HW] : [B*HW, C]  = normalise(codebook)[idx] */
+int vlg_codebook_gather(const int64_t* idx_dev, const float* codebook_dev, float* out_dev, int64_t B, int C,
+                        int64_t HW, int n_e, int l2_norm, int channel_first, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Sampling -- replaces decode_one_token's CFG mix (generate.py:95-99), top_k_top_p_filtering
+ * (generate.py:16-54) and sample (generate.py:57-66).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+  float cfg_scale;     /* logits = uncond + (cond - uncond) * cfg_scale when rows == 2*B and guided */
+  int guided;          /* 0: take the conditional half unchanged (cfg_interval passed, generate.py:98-99) */
+  float temperature;   /* logits / max(temperature, 1e-5) */
+  int top_k;           /* 0 = off; threshold = k-th largest, strict '<' removed (ties survive) */
+  float top_p;         /* 1.0 = off */
+  int sample_logits;   /* 1: multinomial (argmax of probs / Exp(1));  0: argmax(probs) */
+  uint64_t seed;       /* Philox seed for the in-kernel Exp(1) draws (used when noise_dev == NULL) */
+  uint64_t offset;     /* per-call stream offset (the decode loop passes the step index) */
+} vlg_sample_params;
+
+/* logits_dev fp32 [rows, V]   rows = 2*B (cond rows first, then uncond) or rows = B
+ * noise_dev  fp32 [B, V] Exp(1) draws, or NULL to draw in-kernel (Philox4x32-10)
+ * idx_dev    int64 [B]        chosen token
+ * probs_dev  fp32 [B, V] softmax after filtering, or NULL to skip the write                   */
+int vlg_cfg_sample(const float* logits_dev, int rows, int B, int V, const vlg_sample_params* p,
+                   const float* noise_dev, int64_t* idx_dev, float* probs_dev, void* stream);
+
+/* top_k_top_p_filtering alone (generate.py:16-54): out_dev fp32 [B, V] = logits with removed entries at -inf */
+int vlg_top_k_top_p(const float* logits_dev, float* out_dev, int B, int V, int top_k, float top_p, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Decode context -- replaces Transformer.setup_caches (gpt.py:318-332), the inference branch of
+ * Transformer.forward (gpt.py:349-371; gpt_video.py:403-431 for t2v) and the generate() loop
+ * (generate.py:127-180).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+  int dim, n_layer, n_head, hidden_dim;
+  int vocab_size;      /* V (logit width); unused for t2v */
+  int cls_token_num;   /* T: 1 for c2i, 120 for t2i/t2v */
+  int num_classes;     /* c2i: the null class id used for the unconditional rows (generate.py:131) */
+  int caption_dim;     /* t2i/t2v condition width (2048) */
+  int vae_embed_dim;   /* t2v latent width (8) */
+  int model_type;      /* vlg_model_type */
+  int dtype;           /* vlg_dtype of weights, activations and KV cache */
+  float norm_eps;
+} vlg_geometry;
+
+typedef struct {
+  const void* attention_norm; /* [dim] */
+  const void* wqkv;           /* [3*dim, dim]   attention.wqkv.weight */
+  const void* wo;             /* [dim, dim] */
+  const void* ffn_norm;       /* [dim] */
+  const void* w13;            /* [2*hidden, dim] rows interleaved: 2j = w1[j], 2j+1 = w3[j] */
+  const void* w2;             /* [dim, hidden] */
+} vlg_layer_weights;
+
+typedef struct {
+  const void* tok_embeddings;  /* [V, dim]                         (c2i, t2i) */
+  const void* cls_table;       /* [num_classes+1, dim]             (c2i) */
+  const void* cap_fc1;         /* [dim, caption_dim]               (t2i, t2v) */
+  const void* cap_fc2;         /* [dim, dim] */
+  const void* adapter_in_fc1;  /* [dim, vae_embed_dim]             (t2v) vae_latent_adapter */
+  const void* adapter_in_fc2;  /* [dim, dim] */
+  const void* adapter_out_fc1; /* [dim, dim]                       (t2v) vae_latent_adapter2 */
+  const void* adapter_out_fc2; /* [vae_embed_dim, dim] */
+  const void* norm;            /* [dim] */
+  const void* output;          /* [V, dim] */
+  const float* rope_table;     /* fp32 [rope_rows, head_dim/2, 2] (cos, sin): gpt.py:407-420 / gpt_video.py:532-552 */
+  int rope_rows;
+  const vlg_layer_weights* layers; /* [n_layer] (host array, copied) */
+} vlg_weights;
+
+typedef struct vlg_ctx vlg_ctx;
+
+/* bytes of device workspace a context needs for `max_rows` rows (2*B with CFG) and `max_seq` slots */
+size_t vlg_ctx_workspace_bytes(const vlg_geometry* g, int max_rows, int max_seq);
+
+/* Weight pointers are borrowed (device memory, dtype g->dtype, layouts above) and must outlive the
+ * context.  workspace_dev: >= vlg_ctx_workspace_bytes, 1024-byte aligned.  Synchronises once. */
+int vlg_ctx_create(const vlg_geometry* g, const vlg_weights* w, int max_rows, int max_seq, void* workspace_dev,
+                   size_t workspace_bytes, vlg_ctx** out);
+void vlg_ctx_destroy(vlg_ctx* ctx);
+
+/* Start a sequence batch: `rows` cache rows (cond rows then uncond rows when CFG is on).
+ * prefix_mask_dev: uint8 [rows, cls_token_num], 1 = key visible (emb_masks, generate.py:156-165), or NULL. */
+int vlg_begin(vlg_ctx* ctx, int rows, const uint8_t* prefix_mask_dev, void* stream);
+
+/* One position of Transformer.forward's inference branch for all rows (seqlen 1):
+ * exactly one of the three inputs is non-NULL
+ *   tokens_dev  int64 [rows]                      -> tok_embeddings gather   (gpt.py:354)
+ *   labels_dev  int64 [rows]                      -> cls_embedding gather    (gpt.py:352, c2i)
+ *   embeds_dev  dtype [rows, dim]                 -> already-projected prefix embedding / adapter output
+ * pos: cache slot / RoPE row.  logits_dev: fp32 [rows, V] (or NULL to skip the head).
+ * hidden_dev: dtype [rows, dim] final-normed hidden state (or NULL).                          */
+int vlg_forward_pos(vlg_ctx* ctx, const int64_t* tokens_dev, const int64_t* labels_dev, const void* embeds_dev,
+                    int pos, float* logits_dev, void* hidden_dev, void* stream);
+
+/* Caption / latent projection MLP fc2(gelu_tanh(fc1 x)) (gpt.py:118-131): which = 0 cap_proj,
+ * 1 vae_latent_adapter, 2 vae_latent_adapter2.  x_dev dtype [n, in], out_dev dtype [n, out]. */
+int vlg_mlp(vlg_ctx* ctx, int which, const void* x_dev, void* out_dev, int n, void* stream);
+
+/* The whole of generate() for c2i / t2i with device-resident inputs (generate.py:127-180):
+ *   c2i: cond_dev int64 [B] class labels;  t2i: cond_dev dtype [B, T, caption_dim] (+ uncond rows built inside
+ *   from uncond_dev dtype [T, caption_dim] when cfg_scale > 1) and emb_masks_dev uint8 [B, T] or NULL.
+ * tokens_dev int32 [B, max_new_tokens] receives the sequence.  No host synchronisation. */
+typedef struct {
+  int B;
+  int max_new_tokens;
+  float cfg_scale;     /* > 1 doubles the rows (generate.py:130-141) */
+  int cfg_interval;    /* -1 = guide every step (generate.py:113-114) */
+  float temperature;
+  int top_k;
+  float top_p;
+  int sample_logits;
+  uint64_t seed;
+} vlg_generate_params;
+
+int vlg_generate(vlg_ctx* ctx, const vlg_generate_params* p, const void* cond_dev, const void* uncond_dev,
+                 const uint8_t* emb_masks_dev, int32_t* tokens_dev, void* stream);
+
+/* Same with HOST buffers (pinned or pageable): copies cond in, runs, copies tokens out and synchronises
+ * the stream.  This is the call the end-to-end benchmark times. c2i only (labels int64 [B]). */
+int vlg_generate_c2i_host(vlg_ctx* ctx, const vlg_generate_params* p, const int64_t* labels_host,
+                          int32_t* tokens_host, void* stream);
+
+/* number of kernels launched by this library since load (for bench.py's gpu_launches) */
+uint64_t vlg_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Building blocks exposed for unit parity tests (each mirrors one reference op).
+ * dtype = vlg_dtype of x / w / out unless stated.
+ * ------------------------------------------------------------------------------------------ */
+/* RMSNorm (gpt.py:143-148): out = T( T(x * rsqrt(mean(x^2)+eps)) * w ) */
+int vlg_rmsnorm(const void* x_dev, const void* w_dev, void* out_dev, int rows, int dim, float eps, int dtype,
+                void* stream);
+
+/* out[rows,N] = x[rows,K] . w[N,K]^T  (nn.Linear, bias-free).  bf16: tcgen05 tensor cores, fp32 accumulate,
+ * one rounding to bf16.  fp32: CUDA-core FMA, no TF32.  out_f32 != 0 widens the bf16 result to fp32
+ * (`.float()` after the head, gpt.py:371). */
+int vlg_linear(const void* x_dev, const void* w_dev, void* out_dev, int rows, int N, int K, int dtype, int out_f32,
+               void* stream);
+
+/* Single-position attention over the cache prefix [0, pos] (gpt.py:221-239 at seqlen 1, math SDPA):
+ * q_dev dtype [rows, H, D]; k_cache/v_cache dtype [rows, H, S_max, D]; prefix_mask as in vlg_begin;
+ * out_dev dtype [rows, H*D].  impl: 0 = auto, 1 = generic (any dtype), 2 = TMA streaming (bf16 only). */
+int vlg_attn_decode(const void* q_dev, const void* k_cache_dev, const void* v_cache_dev, void* out_dev, int rows,
+                    int H, int D, int S_max, int pos, const uint8_t* prefix_mask_dev, int T_prefix, int dtype,
+                    int impl, void* scratch_dev, size_t scratch_bytes, void* stream);
+size_t vlg_attn_scratch_bytes(int rows, int H, int D, int S_max);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VLG_H_ */

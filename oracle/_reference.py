@@ -45,11 +45,17 @@ class _RefPath:
                       if k.split(".")[0] in self._PKGS}
         for k in self.saved:
             del sys.modules[k]
+        # The reference's packages have no __init__.py (namespace packages), so a regular package of the same
+        # name anywhere on sys.path -- the product's drop-in shims -- would win regardless of order: hide it.
+        self.hidden = [p for p in sys.path if os.path.isfile(os.path.join(p, "autoregressive", "__init__.py"))]
+        for p in self.hidden:
+            sys.path.remove(p)
         sys.path.insert(0, root())
         return self
 
     def __exit__(self, *exc):
         sys.path.remove(root())
+        sys.path[0:0] = self.hidden
         self.ref_modules = {k: v for k, v in sys.modules.items()
                             if k.split(".")[0] in self._PKGS}
         for k in self.ref_modules:

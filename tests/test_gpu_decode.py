@@ -1,0 +1,152 @@
+"""GPU: the decode path end to end (drop-in API -> C ABI -> kernels) against reference-generated fixtures and the
+oracle running on the same device."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ar_decode as O
+from vlg.gpt import Transformer, ModelArgs, GPT_models
+from vlg.generate import generate, prefill, decode_n_tokens, sample
+from helpers import weights_from, TINY_C2I, TINY_T2I
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+# bf16 logit tolerance: the reference's own bf16-vs-fp32 noise floor is rms 0.0056 / max 0.031
+# on raw logits of rms 0.55; two bf16 implementations differ by summation order at every rounding point.
+BF16_ATOL, BF16_RTOL = 0.06, 0.02
+
+
+def setup_module(module):
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    torch.set_float32_matmul_precision("highest")
+
+
+def tiny_model(f, args):
+    m = Transformer(args).eval()
+    m.load_state_dict({k[2:]: torch.from_numpy(f[k]) for k in f.files if k.startswith("w.")}, strict=True)
+    return m
+
+
+C2I_ARGS = dict(dim=128, n_layer=2, n_head=2, vocab_size=512, block_size=16, multiple_of=64, cls_token_num=1,
+                num_classes=10, model_type="c2i")
+T2I_ARGS = dict(dim=128, n_layer=2, n_head=2, vocab_size=256, block_size=16, multiple_of=64, cls_token_num=120,
+                caption_dim=32, model_type="t2i")
+
+
+def teacher_forced(model, rows_cond, tokens, T):
+    """Step Transformer.forward like the reference's callers do; returns raw logits [N, R, V]."""
+    R = rows_cond.shape[0]
+    N = tokens.shape[1] + 1
+    model.setup_caches(R, T + N, None)
+    out = [model(None, rows_cond, torch.arange(T, device=DEV))[0][:, -1]]
+    for i in range(N - 1):
+        x = torch.cat([tokens[:, i:i + 1], tokens[:, i:i + 1]])
+        out.append(model(x, None, torch.tensor([T + i], device=DEV))[0][:, -1])
+    return torch.stack(out)
+
+
+def test_c2i_tiny_fp32_logits_and_greedy(golden):
+    f = golden("c2i_tiny.npz")
+    m = tiny_model(f, ModelArgs(**C2I_ARGS)).to(DEV)
+    cond = torch.from_numpy(f["cond"]).to(DEV)
+    rows = torch.cat([cond, torch.ones_like(cond) * 10])
+    logits = teacher_forced(m, rows, torch.from_numpy(f["tokens"]).to(DEV), 1)
+    assert np.abs(logits.cpu().numpy() - f["logits"]).max() < 1e-4
+    g = generate(m, cond, 16, cfg_scale=4.0, temperature=1.0, top_k=1, top_p=1.0, sample_logits=False)
+    assert g.dtype == torch.int32 and np.array_equal(g.cpu().numpy(), f["greedy"])
+    g = generate(m, cond, 16, cfg_scale=1.0, temperature=1.0, top_k=0, top_p=1.0, sample_logits=False)
+    assert np.array_equal(g.cpu().numpy(), f["greedy_nocfg"])
+    g = generate(m, cond, 16, cfg_scale=3.0, cfg_interval=5, temperature=1.0, top_k=0, top_p=1.0, sample_logits=False)
+    assert np.array_equal(g.cpu().numpy(), f["greedy_interval"])
+
+
+def test_c2i_tiny_python_driven_loop_matches_fused_loop(golden):
+    """prefill + decode_n_tokens (reference call pattern, generate.py:170-178) == in-library graph loop."""
+    f = golden("c2i_tiny.npz")
+    m = tiny_model(f, ModelArgs(**C2I_ARGS)).to(DEV)
+    cond = torch.from_numpy(f["cond"]).to(DEV)
+    kw = dict(temperature=1.0, top_k=1, top_p=1.0, sample_logits=False)
+    m.setup_caches(6, 1 + 16, None)
+    rows = torch.cat([cond, torch.ones_like(cond) * 10])
+    tok = prefill(m, rows, torch.arange(1, device=DEV), 4.0, **kw)
+    toks, probs = decode_n_tokens(m, tok, torch.tensor([1], device=DEV, dtype=torch.int), 15, 4.0, -1, **kw)
+    seq = torch.cat([tok] + toks, dim=1)
+    assert np.array_equal(seq.cpu().numpy(), f["greedy"])
+    assert probs[0].shape == (3, 512)
+
+
+def test_t2i_tiny_masked_prefix_fp32(golden):
+    f = golden("t2i_tiny.npz")
+    m = tiny_model(f, ModelArgs(**T2I_ARGS)).to(DEV)
+    cond = torch.from_numpy(f["cond"]).to(DEV)
+    masks = torch.from_numpy(f["emb_masks"]).to(DEV)
+    g = generate(m, cond, 16, emb_masks=masks, cfg_scale=4.0, temperature=1.0, top_k=1, top_p=1.0, sample_logits=False)
+    assert np.array_equal(g.cpu().numpy(), f["greedy"])
+    # teacher-forced logits through the step API with the prefix mask installed
+    rows = torch.cat([cond, torch.zeros_like(cond) + m.cls_embedding.uncond_embedding])
+    R, T, N = 6, 120, 16
+    m.setup_caches(R, T + N, None)
+    m.set_prefix_mask(torch.cat([masks, masks]))
+    out = [m(None, rows, torch.arange(T, device=DEV))[0][:, -1]]
+    toks = torch.from_numpy(f["tokens"]).to(DEV)
+    for i in range(N - 1):
+        x = torch.cat([toks[:, i:i + 1], toks[:, i:i + 1]])
+        out.append(m(x, None, torch.tensor([T + i], device=DEV))[0][:, -1])
+    assert np.abs(torch.stack(out).cpu().numpy() - f["logits"]).max() < 1e-4
+
+
+def test_c2i_tiny_bf16_logits_within_tolerance(golden):
+    f = golden("c2i_tiny.npz")
+    m = tiny_model(f, ModelArgs(**C2I_ARGS)).to(DEV, torch.bfloat16)
+    cond = torch.from_numpy(f["cond"]).to(DEV)
+    toks = torch.from_numpy(f["tokens"]).to(DEV)
+    rows = torch.cat([cond, torch.ones_like(cond) * 10])
+    ours = teacher_forced(m, rows, toks, 1).float()
+    w16 = weights_from(f, torch.bfloat16, DEV)
+    ref = O.teacher_forced_logits(TINY_C2I, w16, cond, toks)           # oracle on the GPU, bf16 library kernels
+    gold = torch.from_numpy(f["logits"]).to(DEV)                       # fp32 reference
+    assert torch.allclose(ours, ref, rtol=BF16_RTOL, atol=BF16_ATOL), (ours - ref).abs().max()
+    rms_ours = (ours - gold).pow(2).mean().sqrt().item()
+    rms_ref = (ref - gold).pow(2).mean().sqrt().item()
+    assert rms_ours <= 1.5 * rms_ref + 1e-4, (rms_ours, rms_ref)       # no noisier than the reference's own bf16 run
+
+
+def test_gptb_fp32_greedy_matches_reference(golden):
+    """cfg-1 geometry (GPT-B c2i 256 px, CFG 4.0), weights recreated from the seed by the drop-in constructor."""
+    f = golden("gptb_greedy.npz")
+    torch.manual_seed(0)
+    m = GPT_models["GPT-B"](block_size=256, cls_token_num=1, model_type="c2i").eval()
+    torch.nn.init.normal_(m.output.weight, std=0.02)
+    m = m.to(DEV)
+    cond = torch.from_numpy(f["cond"]).to(DEV)
+    g = generate(m, cond, 24, cfg_scale=4.0, temperature=1.0, top_k=1, top_p=1.0, sample_logits=False)
+    assert np.array_equal(g.cpu().numpy(), f["greedy"])
+
+
+def test_gptl_cfg2_full_size_bf16():
+    """BASELINE cfg-2: GPT-L c2i 384 px, batch 64 with CFG (128 rows), 576 tokens, bf16, top-k 2000.
+    Full-size checks: runs, tokens valid, deterministic per seed, and teacher-forced logits at positions spread over
+    the sequence agree with the oracle run on the same GPU."""
+    geo = O.Geometry(block_size=576, **O.NAMED["GPT-L"])
+    w = O.init_weights(geo, seed=0, dtype=torch.float32, embed_std=0.3)
+    m = GPT_models["GPT-L"](block_size=576, cls_token_num=1, model_type="c2i").eval()
+    m.load_state_dict(w, strict=True)
+    m = m.to(DEV, torch.bfloat16)
+    cond = torch.randint(0, 1000, (64,), generator=torch.Generator().manual_seed(1234)).to(DEV)
+    kw = dict(cfg_scale=4.0, temperature=1.0, top_k=2000, top_p=1.0, sample_logits=True)
+    a = generate(m, cond, 576, seed=7, **kw)
+    b = generate(m, cond, 576, seed=7, **kw)
+    c = generate(m, cond, 576, seed=8, **kw)
+    assert a.shape == (64, 576) and int(a.min()) >= 0 and int(a.max()) < 16384
+    assert torch.equal(a, b) and not torch.equal(a, c)
+    assert len(torch.unique(a)) > 1000                                 # real sampling, not a collapsed cycle
+    # teacher-forced: feed the generated stream back, compare raw logits with the oracle on 8 samples (16 rows)
+    sub = cond[:8]
+    toks = a[:8, :40].long()
+    w16 = {k: v.to(DEV, torch.bfloat16) for k, v in w.items()}
+    ref = O.teacher_forced_logits(geo, w16, sub, toks)
+    rows = torch.cat([sub, torch.ones_like(sub) * 1000])
+    ours = teacher_forced(m, rows, toks, 1).float()
+    assert torch.allclose(ours, ref, rtol=BF16_RTOL, atol=BF16_ATOL), (ours - ref).abs().max()

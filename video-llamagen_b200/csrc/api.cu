@@ -1,0 +1,443 @@
+// Decode context: workspace layout, one-position forward, and the whole generate() loop as a CUDA graph.
+//
+// Replaces Transformer.setup_caches (gpt.py:318-332), the inference branch of Transformer.forward
+// (gpt.py:349-371) and generate()/prefill/decode_n_tokens (generate.py:77-180).  The loop state (step
+// counter, cache position, RNG seed) lives in device memory and is advanced by the sampler kernel, so a
+// decode step is a fixed kernel sequence: it is captured once into a CUDA graph and replayed N-1 times
+// with no host synchronisation and no per-step host work besides cudaGraphLaunch.
+#include <stdlib.h>
+#include <vector>
+
+#include "common.cuh"
+#include "kernels.h"
+
+using namespace vlg;
+
+namespace {
+
+struct StepState {      // device-resident loop state (ints)
+  int step;             // index of the token being produced (column of seq)
+  int pos;              // cache slot / RoPE row of the current input
+  unsigned done_ctr;    // sampler CTA completion counter
+  int pad;
+};
+
+size_t esz(int dtype) { return dtype == VLG_BF16 ? 2 : 4; }
+size_t align_up(size_t v, size_t a = 1024) { return (v + a - 1) / a * a; }
+int round8(int n) { return (n + 7) / 8 * 8; }
+
+struct Layout {
+  size_t k_cache, v_cache, h, xn, q, attn, ffn, logits, attn_scratch, state, mask, seq, labels, cond_rows, prefix_emb,
+      mlp_tmp, total;
+};
+
+Layout make_layout(const vlg_geometry& g, int max_rows, int max_seq) {
+  Layout L{};
+  const size_t e = esz(g.dtype);
+  const int S = round8(max_seq), D = g.dim / g.n_head;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes); return o; };
+  const size_t kv = (size_t)g.n_layer * max_rows * g.n_head * S * D * e;
+  L.k_cache = take(kv);
+  L.v_cache = take(kv);
+  L.h = take((size_t)max_rows * g.dim * e);
+  L.xn = take((size_t)max_rows * g.dim * e);
+  L.q = take((size_t)max_rows * g.dim * e);
+  L.attn = take((size_t)max_rows * g.dim * e);
+  L.ffn = take((size_t)max_rows * g.hidden_dim * e);
+  L.logits = take((size_t)max_rows * (g.vocab_size > 0 ? g.vocab_size : 1) * 4);
+  L.attn_scratch = take(attn_scratch_bytes(max_rows, g.n_head, D, S));
+  L.state = take(sizeof(StepState));
+  L.mask = take((size_t)max_rows * g.cls_token_num);
+  L.seq = take((size_t)max_rows * S * sizeof(int32_t));
+  L.labels = take((size_t)max_rows * sizeof(int64_t));
+  if (g.model_type != VLG_C2I) {
+    L.cond_rows = take((size_t)max_rows * g.cls_token_num * g.caption_dim * e);   // raw condition rows (cond + uncond)
+    L.prefix_emb = take((size_t)max_rows * g.cls_token_num * g.dim * e);          // cap_proj output
+    L.mlp_tmp = take((size_t)max_rows * g.cls_token_num * g.dim * e);             // fc1 + GELU intermediate
+  }
+  L.total = off;
+  return L;
+}
+
+}  // namespace
+
+struct vlg_ctx {
+  vlg_geometry g;
+  vlg_weights w;
+  std::vector<vlg_layer_weights> layers;
+  int max_rows, S_max, D;
+  uint8_t* ws;
+  Layout L;
+  // current sequence batch
+  int rows = 0;
+  bool has_mask = false;
+  bool force_generic_attn = false;   // VLG_ATTN=generic: A/B the two attention kernels
+  // cached decode-step graph
+  cudaGraphExec_t graph = nullptr;
+  uint64_t step_kernels = 0;   // kernels per replayed decode step
+  struct Key { int rows, B, N, top_k, sample_logits, cfg_interval, has_mask; float cfg_scale, temperature, top_p; uint64_t seed; } key{};
+
+  template <typename T> T* at(size_t off) const { return reinterpret_cast<T*>(ws + off); }
+  void* kc(int layer) const { return ws + L.k_cache + (size_t)layer * max_rows * g.n_head * S_max * D * esz(g.dtype); }
+  void* vc(int layer) const { return ws + L.v_cache + (size_t)layer * max_rows * g.n_head * S_max * D * esz(g.dtype); }
+  StepState* state() const { return at<StepState>(L.state); }
+};
+
+namespace {
+
+__global__ void set_state_kernel(StepState* s, int step, int pos) {
+  s->step = step;
+  s->pos = pos;
+  s->done_ctr = 0;
+}
+
+// rows [0,B) <- cond[b], rows [B,2B) <- uncond (broadcast): generate.py:137-139
+template <typename T>
+__global__ void build_cond_rows_kernel(const T* __restrict__ cond, const T* __restrict__ uncond, T* __restrict__ out,
+                                       int B, size_t per_row) {
+  const int r = blockIdx.y;
+  const T* src = r < B ? cond + (size_t)r * per_row : uncond;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < per_row; i += (size_t)gridDim.x * blockDim.x)
+    out[(size_t)r * per_row + i] = src[i];
+}
+__global__ void build_mask_rows_kernel(const uint8_t* __restrict__ m, uint8_t* __restrict__ out, int B, int T, int rows) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < rows * T) out[i] = m[(size_t)((i / T) % B) * T + (i % T)];
+}
+// h[r] <- prefix_emb[r, t]
+template <typename T>
+__global__ void take_prefix_kernel(const T* __restrict__ emb, T* __restrict__ h, int Tn, int t, int dim) {
+  const int r = blockIdx.x;
+  const uint4* src = reinterpret_cast<const uint4*>(emb + ((size_t)r * Tn + t) * dim);
+  uint4* dst = reinterpret_cast<uint4*>(h + (size_t)r * dim);
+  for (int i = threadIdx.x; i < dim * (int)sizeof(T) / 16; i += blockDim.x) dst[i] = src[i];
+}
+
+// N transformer blocks on ctx->h (in place); final-normed hidden left in ctx->xn.
+int run_trunk(vlg_ctx* c, const int* pos_ptr, int pos_imm, int max_pos, cudaStream_t st) {
+  const vlg_geometry& g = c->g;
+  const int R = c->rows, d = g.dim, hid = g.hidden_dim;
+  void* h = c->at<void>(c->L.h);
+  void* xn = c->at<void>(c->L.xn);
+  void* q = c->at<void>(c->L.q);
+  void* attn = c->at<void>(c->L.attn);
+  void* ffn = c->at<void>(c->L.ffn);
+  int rc;
+  for (int l = 0; l < g.n_layer; ++l) {
+    const vlg_layer_weights& lw = c->layers[l];
+    if ((rc = launch_rmsnorm(g.dtype, h, lw.attention_norm, xn, R, d, g.norm_eps, st))) return rc;
+    EpiParams P{};
+    P.q_out = q; P.k_cache = c->kc(l); P.v_cache = c->vc(l);
+    P.rope = c->w.rope_table; P.pos_ptr = pos_ptr; P.pos_imm = pos_imm;
+    P.S_max = c->S_max; P.H = g.n_head; P.D = c->D; P.dim = d;
+    if ((rc = launch_gemm(g.dtype, EPI_QKV_ROPE, xn, lw.wqkv, R, 3 * d, d, P, st))) return rc;
+    AttnArgs a{};
+    a.q = q; a.k_cache = c->kc(l); a.v_cache = c->vc(l); a.out = attn;
+    a.rows = R; a.H = g.n_head; a.D = c->D; a.S_max = c->S_max;
+    a.pos_ptr = pos_ptr; a.pos_imm = pos_imm; a.max_pos = max_pos;
+    a.prefix_mask = c->has_mask ? c->at<uint8_t>(c->L.mask) : nullptr;
+    a.T_prefix = c->has_mask ? g.cls_token_num : 0;
+    a.scratch = c->at<float>(c->L.attn_scratch);
+    a.scratch_bytes = attn_scratch_bytes(c->max_rows, g.n_head, c->D, c->S_max);
+    rc = (g.dtype == VLG_BF16 && !c->force_generic_attn) ? launch_attn_tma(g.dtype, a, st) : launch_attn_generic(g.dtype, a, st);
+    if (rc) return rc;
+    EpiParams Po{};
+    Po.out = h; Po.ld_out = d; Po.resid = h;
+    if ((rc = launch_gemm(g.dtype, EPI_RESID, attn, lw.wo, R, d, d, Po, st))) return rc;
+    if ((rc = launch_rmsnorm(g.dtype, h, lw.ffn_norm, xn, R, d, g.norm_eps, st))) return rc;
+    EpiParams Pf{};
+    Pf.out = ffn; Pf.ld_out = hid;
+    if ((rc = launch_gemm(g.dtype, EPI_SWIGLU, xn, lw.w13, R, 2 * hid, d, Pf, st))) return rc;
+    EpiParams P2{};
+    P2.out = h; P2.ld_out = d; P2.resid = h;
+    if ((rc = launch_gemm(g.dtype, EPI_RESID, ffn, lw.w2, R, d, hid, P2, st))) return rc;
+  }
+  return launch_rmsnorm(g.dtype, h, c->w.norm, xn, R, d, g.norm_eps, st);
+}
+
+int run_head(vlg_ctx* c, float* logits, cudaStream_t st) {
+  EpiParams P{};
+  P.out = logits;
+  P.ld_out = c->g.vocab_size;
+  return launch_gemm(c->g.dtype, EPI_STORE_F32, c->at<void>(c->L.xn), c->w.output, c->rows, c->g.vocab_size, c->g.dim, P, st);
+}
+
+SampleArgs loop_sample_args(vlg_ctx* c, const vlg_generate_params& p) {
+  SampleArgs a{};
+  a.logits = c->at<float>(c->L.logits);
+  a.rows = c->rows;
+  a.B = p.B;
+  a.V = c->g.vocab_size;
+  a.p.cfg_scale = p.cfg_scale;
+  a.p.guided = 1;
+  a.p.temperature = p.temperature;
+  a.p.top_k = p.top_k;
+  a.p.top_p = p.top_p;
+  a.p.sample_logits = p.sample_logits;
+  a.p.seed = p.seed;
+  a.p.offset = 0;
+  a.seq_out = c->at<int32_t>(c->L.seq);
+  a.seq_stride = p.max_new_tokens;
+  a.step_ptr = &c->state()->step;
+  a.pos_ptr = &c->state()->pos;
+  a.cfg_interval = p.cfg_interval;
+  a.done_ctr = &c->state()->done_ctr;
+  return a;
+}
+
+// one decode step: token gather -> trunk -> head -> sample (advances the device state)
+int decode_step(vlg_ctx* c, const vlg_generate_params& p, cudaStream_t st) {
+  const vlg_geometry& g = c->g;
+  int rc = launch_gather(g.dtype, c->w.tok_embeddings, c->at<void>(c->L.h), c->rows, g.dim, nullptr,
+                         c->at<int32_t>(c->L.seq), p.max_new_tokens, &c->state()->step, -1, nullptr, p.B, 0,
+                         g.vocab_size, st);
+  if (rc) return rc;
+  if ((rc = run_trunk(c, &c->state()->pos, 0, g.cls_token_num + p.max_new_tokens - 1, st))) return rc;
+  if ((rc = run_head(c, c->at<float>(c->L.logits), st))) return rc;
+  return launch_sample(loop_sample_args(c, p), st);
+}
+
+}  // namespace
+
+extern "C" size_t vlg_ctx_workspace_bytes(const vlg_geometry* g, int max_rows, int max_seq) {
+  if (!g || max_rows <= 0 || max_seq <= 0 || g->n_head <= 0) return 0;
+  return make_layout(*g, max_rows, max_seq).total;
+}
+
+extern "C" int vlg_ctx_create(const vlg_geometry* g, const vlg_weights* w, int max_rows, int max_seq,
+                              void* workspace_dev, size_t workspace_bytes, vlg_ctx** out) {
+  VLG_REQUIRE(g && w && out && workspace_dev, "vlg_ctx_create: null pointer");
+  VLG_REQUIRE(g->dtype == VLG_F32 || g->dtype == VLG_BF16, "vlg_ctx_create: bad dtype %d", g->dtype);
+  VLG_REQUIRE(g->dim > 0 && g->n_head > 0 && g->dim % g->n_head == 0 && g->dim / g->n_head == 64,
+              "vlg_ctx_create: head_dim must be 64 (dim=%d n_head=%d)", g->dim, g->n_head);
+  VLG_REQUIRE(g->hidden_dim % 32 == 0 && g->dim % 64 == 0, "vlg_ctx_create: dim %% 64 and hidden %% 32 required");
+  VLG_REQUIRE(max_rows > 0 && max_seq > 0, "vlg_ctx_create: bad sizes");
+  VLG_REQUIRE((reinterpret_cast<uintptr_t>(workspace_dev) & 1023) == 0, "vlg_ctx_create: workspace must be 1024-byte aligned");
+  int dev = 0, major = 0;
+  VLG_CUDA(cudaGetDevice(&dev));
+  VLG_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  if (major != 10) {
+    set_error("vlg_ctx_create: device compute capability %d.x is not sm_100 (B200); there is no fallback path", major);
+    return VLG_ERR_UNSUPPORTED;
+  }
+  Layout L = make_layout(*g, max_rows, max_seq);
+  VLG_REQUIRE(workspace_bytes >= L.total, "vlg_ctx_create: workspace %zu < required %zu bytes", workspace_bytes, L.total);
+  VLG_REQUIRE(w->layers && w->norm && w->rope_table && w->rope_rows >= round8(max_seq) - 7,
+              "vlg_ctx_create: missing weights or RoPE table too short (%d rows)", w->rope_rows);
+  vlg_ctx* c = new vlg_ctx();
+  c->g = *g;
+  c->w = *w;
+  c->layers.assign(w->layers, w->layers + g->n_layer);
+  c->w.layers = c->layers.data();
+  c->max_rows = max_rows;
+  c->S_max = round8(max_seq);
+  c->D = g->dim / g->n_head;
+  c->ws = static_cast<uint8_t*>(workspace_dev);
+  c->L = L;
+  const char* env = getenv("VLG_ATTN");
+  c->force_generic_attn = env && strcmp(env, "generic") == 0;
+  // the reference allocates zeroed caches (gpt.py:174-175); do it once so no stale NaN bit patterns exist
+  VLG_CUDA(cudaMemset(c->ws + L.k_cache, 0, L.h - L.k_cache));
+  VLG_CUDA(cudaMemset(c->state(), 0, sizeof(StepState)));
+  VLG_CUDA(cudaDeviceSynchronize());
+  *out = c;
+  return VLG_OK;
+}
+
+extern "C" void vlg_ctx_destroy(vlg_ctx* c) {
+  if (!c) return;
+  if (c->graph) cudaGraphExecDestroy(c->graph);
+  delete c;
+}
+
+extern "C" int vlg_begin(vlg_ctx* c, int rows, const uint8_t* prefix_mask_dev, void* stream) {
+  VLG_REQUIRE(c, "vlg_begin: null ctx");
+  VLG_REQUIRE(rows > 0 && rows <= c->max_rows, "vlg_begin: rows %d outside (0, %d]", rows, c->max_rows);
+  cudaStream_t st = (cudaStream_t)stream;
+  c->rows = rows;
+  c->has_mask = prefix_mask_dev != nullptr;
+  if (prefix_mask_dev)
+    VLG_CUDA(cudaMemcpyAsync(c->at<uint8_t>(c->L.mask), prefix_mask_dev, (size_t)rows * c->g.cls_token_num,
+                             cudaMemcpyDeviceToDevice, st));
+  set_state_kernel<<<1, 1, 0, st>>>(c->state(), 0, 0);
+  VLG_LAUNCH_CHECK();
+  return VLG_OK;
+}
+
+extern "C" int vlg_forward_pos(vlg_ctx* c, const int64_t* tokens_dev, const int64_t* labels_dev, const void* embeds_dev,
+                               int pos, float* logits_dev, void* hidden_dev, void* stream) {
+  VLG_REQUIRE(c && c->rows > 0, "vlg_forward_pos: call vlg_begin first");
+  VLG_REQUIRE((tokens_dev != nullptr) + (labels_dev != nullptr) + (embeds_dev != nullptr) == 1,
+              "vlg_forward_pos: exactly one of tokens / labels / embeds must be given");
+  VLG_REQUIRE(pos >= 0 && pos < c->S_max && pos < c->w.rope_rows, "vlg_forward_pos: pos %d out of range", pos);
+  cudaStream_t st = (cudaStream_t)stream;
+  const vlg_geometry& g = c->g;
+  int rc = VLG_OK;
+  if (tokens_dev) {
+    VLG_REQUIRE(c->w.tok_embeddings, "vlg_forward_pos: no tok_embeddings");
+    rc = launch_gather(g.dtype, c->w.tok_embeddings, c->at<void>(c->L.h), c->rows, g.dim, tokens_dev, nullptr, 0,
+                       nullptr, 0, nullptr, 1, 0, g.vocab_size, st);
+  } else if (labels_dev) {
+    VLG_REQUIRE(c->w.cls_table, "vlg_forward_pos: no class table (model is not c2i)");
+    rc = launch_gather(g.dtype, c->w.cls_table, c->at<void>(c->L.h), c->rows, g.dim, labels_dev, nullptr, 0, nullptr,
+                       0, nullptr, 1, 0, 1 << 30, st);
+  } else {
+    VLG_CUDA(cudaMemcpyAsync(c->at<void>(c->L.h), embeds_dev, (size_t)c->rows * g.dim * esz(g.dtype),
+                             cudaMemcpyDeviceToDevice, st));
+  }
+  if (rc) return rc;
+  if ((rc = run_trunk(c, nullptr, pos, pos, st))) return rc;
+  if (hidden_dev)
+    VLG_CUDA(cudaMemcpyAsync(hidden_dev, c->at<void>(c->L.xn), (size_t)c->rows * g.dim * esz(g.dtype),
+                             cudaMemcpyDeviceToDevice, st));
+  if (logits_dev) {
+    VLG_REQUIRE(c->w.output && g.vocab_size > 0, "vlg_forward_pos: model has no output head");
+    if ((rc = run_head(c, logits_dev, st))) return rc;
+  }
+  return VLG_OK;
+}
+
+extern "C" int vlg_mlp(vlg_ctx* c, int which, const void* x_dev, void* out_dev, int n, void* stream) {
+  VLG_REQUIRE(c && x_dev && out_dev && n > 0, "vlg_mlp: bad arguments");
+  const vlg_geometry& g = c->g;
+  VLG_REQUIRE(g.model_type != VLG_C2I, "vlg_mlp: c2i models have no projection MLPs");
+  const void *fc1, *fc2;
+  int in, mid = g.dim, outw;
+  switch (which) {
+    case 0: fc1 = c->w.cap_fc1; fc2 = c->w.cap_fc2; in = g.caption_dim; outw = g.dim; break;
+    case 1: fc1 = c->w.adapter_in_fc1; fc2 = c->w.adapter_in_fc2; in = g.vae_embed_dim; outw = g.dim; break;
+    case 2: fc1 = c->w.adapter_out_fc1; fc2 = c->w.adapter_out_fc2; in = g.dim; outw = g.vae_embed_dim; break;
+    default: set_error("vlg_mlp: which=%d", which); return VLG_ERR_ARG;
+  }
+  VLG_REQUIRE(fc1 && fc2, "vlg_mlp: weights for MLP %d not provided", which);
+  VLG_REQUIRE((size_t)n <= (size_t)c->max_rows * g.cls_token_num, "vlg_mlp: n=%d exceeds the staging buffer", n);
+  cudaStream_t st = (cudaStream_t)stream;
+  EpiParams P1{};
+  P1.out = c->at<void>(c->L.mlp_tmp);
+  P1.ld_out = mid;
+  int rc = launch_gemm(g.dtype, EPI_GELU, x_dev, fc1, n, mid, in, P1, st);
+  if (rc) return rc;
+  EpiParams P2{};
+  P2.out = out_dev;
+  P2.ld_out = outw;
+  return launch_gemm(g.dtype, EPI_STORE, c->at<void>(c->L.mlp_tmp), fc2, n, outw, mid, P2, st);
+}
+
+extern "C" int vlg_generate(vlg_ctx* c, const vlg_generate_params* pp, const void* cond_dev, const void* uncond_dev,
+                            const uint8_t* emb_masks_dev, int32_t* tokens_dev, void* stream) {
+  VLG_REQUIRE(c && pp && cond_dev && tokens_dev, "vlg_generate: null pointer");
+  const vlg_generate_params p = *pp;
+  const vlg_geometry& g = c->g;
+  VLG_REQUIRE(g.model_type == VLG_C2I || g.model_type == VLG_T2I, "vlg_generate: model type %d has no token sampler", g.model_type);
+  const bool cfg = p.cfg_scale > 1.0f;
+  const int rows = cfg ? 2 * p.B : p.B;
+  const int T = g.cls_token_num, N = p.max_new_tokens;
+  VLG_REQUIRE(p.B > 0 && rows <= c->max_rows, "vlg_generate: batch %d (rows %d) exceeds max_rows %d", p.B, rows, c->max_rows);
+  VLG_REQUIRE(N > 0 && T + N <= c->S_max && T + N - 1 <= c->w.rope_rows, "vlg_generate: %d new tokens do not fit (S_max %d)", N, c->S_max);
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc;
+
+  // ---- rows, masks, state (generate.py:129-165)
+  c->rows = rows;
+  c->has_mask = emb_masks_dev != nullptr && g.model_type == VLG_T2I;
+  if (c->has_mask) {
+    build_mask_rows_kernel<<<(rows * T + 255) / 256, 256, 0, st>>>(emb_masks_dev, c->at<uint8_t>(c->L.mask), p.B, T, rows);
+    VLG_LAUNCH_CHECK();
+  }
+  set_state_kernel<<<1, 1, 0, st>>>(c->state(), 0, T - 1);
+  VLG_LAUNCH_CHECK();
+
+  // ---- prefill (generate.py:77-86): every conditioning position through the trunk, sample from the last
+  if (g.model_type == VLG_C2I) {
+    VLG_REQUIRE(c->w.cls_table, "vlg_generate: c2i model without class table");
+    if ((rc = launch_gather(g.dtype, c->w.cls_table, c->at<void>(c->L.h), rows, g.dim, nullptr, nullptr, 0, nullptr, 0,
+                            static_cast<const int64_t*>(cond_dev), p.B, g.num_classes, g.num_classes + 1, st)))
+      return rc;
+    if ((rc = run_trunk(c, &c->state()->pos, 0, T + N - 1, st))) return rc;
+  } else {
+    VLG_REQUIRE(!cfg || uncond_dev, "vlg_generate: t2i with cfg_scale > 1 needs the uncond embedding");
+    const size_t per_row = (size_t)T * g.caption_dim;
+    void* rows_in = c->at<void>(c->L.cond_rows);
+    dim3 grid(64, rows);
+    if (g.dtype == VLG_BF16)
+      build_cond_rows_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)cond_dev, (const __nv_bfloat16*)uncond_dev,
+                                                                  (__nv_bfloat16*)rows_in, p.B, per_row);
+    else
+      build_cond_rows_kernel<float><<<grid, 256, 0, st>>>((const float*)cond_dev, (const float*)uncond_dev, (float*)rows_in, p.B, per_row);
+    VLG_LAUNCH_CHECK();
+    if ((rc = vlg_mlp(c, 0, rows_in, c->at<void>(c->L.prefix_emb), rows * T, st))) return rc;
+    for (int t = 0; t < T; ++t) {
+      if (g.dtype == VLG_BF16)
+        take_prefix_kernel<__nv_bfloat16><<<rows, 128, 0, st>>>(c->at<__nv_bfloat16>(c->L.prefix_emb), c->at<__nv_bfloat16>(c->L.h), T, t, g.dim);
+      else
+        take_prefix_kernel<float><<<rows, 128, 0, st>>>(c->at<float>(c->L.prefix_emb), c->at<float>(c->L.h), T, t, g.dim);
+      VLG_LAUNCH_CHECK();
+      if ((rc = run_trunk(c, nullptr, t, T + N - 1, st))) return rc;
+    }
+  }
+  if ((rc = run_head(c, c->at<float>(c->L.logits), st))) return rc;
+  if ((rc = launch_sample(loop_sample_args(c, p), st))) return rc;   // step 0 -> 1, pos T-1 -> T
+
+  // ---- decode loop (generate.py:105-124) as a replayed CUDA graph
+  if (N > 1) {
+    vlg_ctx::Key k{rows, p.B, N, p.top_k, p.sample_logits, p.cfg_interval, c->has_mask ? 1 : 0, p.cfg_scale, p.temperature, p.top_p, p.seed};
+    if (!c->graph || memcmp(&k, &c->key, sizeof(k)) != 0) {
+      if (c->graph) { cudaGraphExecDestroy(c->graph); c->graph = nullptr; }
+      cudaGraph_t graph = nullptr;
+      VLG_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed));
+      const uint64_t launches_before = vlg_launch_count();
+      rc = decode_step(c, p, st);
+      const uint64_t launches_after = vlg_launch_count();
+      count_launches(launches_before - launches_after);   // capture is not execution: undo, replays are counted below
+      cudaError_t e = cudaStreamEndCapture(st, &graph);
+      if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+      VLG_CUDA(e);
+      e = cudaGraphInstantiate(&c->graph, graph, 0);
+      cudaGraphDestroy(graph);
+      VLG_CUDA(e);
+      c->key = k;
+      c->step_kernels = launches_after - launches_before;
+    }
+    for (int i = 0; i < N - 1; ++i) VLG_CUDA(cudaGraphLaunch(c->graph, st));
+    count_launches((uint64_t)(N - 1) * c->step_kernels);
+  }
+  if (tokens_dev != c->at<int32_t>(c->L.seq))
+    VLG_CUDA(cudaMemcpyAsync(tokens_dev, c->at<int32_t>(c->L.seq), (size_t)p.B * N * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+  return VLG_OK;
+}
+
+extern "C" int vlg_generate_c2i_host(vlg_ctx* c, const vlg_generate_params* p, const int64_t* labels_host,
+                                     int32_t* tokens_host, void* stream) {
+  VLG_REQUIRE(c && p && labels_host && tokens_host, "vlg_generate_c2i_host: null pointer");
+  VLG_REQUIRE(c->g.model_type == VLG_C2I, "vlg_generate_c2i_host: model is not c2i");
+  VLG_REQUIRE(p->B > 0 && p->B <= c->max_rows, "vlg_generate_c2i_host: bad batch %d", p->B);
+  cudaStream_t st = (cudaStream_t)stream;
+  int64_t* labels_dev = c->at<int64_t>(c->L.labels);
+  VLG_CUDA(cudaMemcpyAsync(labels_dev, labels_host, (size_t)p->B * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+  // tokens land in the context's seq buffer; vlg_generate's final copy is redirected to it (no extra D2D)
+  int32_t* seq = c->at<int32_t>(c->L.seq);
+  int rc = vlg_generate(c, p, labels_dev, nullptr, nullptr, seq, stream);
+  if (rc) return rc;
+  VLG_CUDA(cudaMemcpyAsync(tokens_host, seq, (size_t)p->B * p->max_new_tokens * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  VLG_CUDA(cudaStreamSynchronize(st));
+  return VLG_OK;
+}
+
+extern "C" int vlg_attn_decode(const void* q_dev, const void* k_cache_dev, const void* v_cache_dev, void* out_dev,
+                               int rows, int H, int D, int S_max, int pos, const uint8_t* prefix_mask_dev, int T_prefix,
+                               int dtype, int impl, void* scratch_dev, size_t scratch_bytes, void* stream) {
+  VLG_REQUIRE(q_dev && k_cache_dev && v_cache_dev && out_dev, "vlg_attn_decode: null pointer");
+  VLG_REQUIRE(pos >= 0 && pos < S_max, "vlg_attn_decode: pos %d outside [0, %d)", pos, S_max);
+  AttnArgs a{};
+  a.q = q_dev; a.k_cache = k_cache_dev; a.v_cache = v_cache_dev; a.out = out_dev;
+  a.rows = rows; a.H = H; a.D = D; a.S_max = S_max;
+  a.pos_ptr = nullptr; a.pos_imm = pos; a.max_pos = pos;
+  a.prefix_mask = prefix_mask_dev; a.T_prefix = prefix_mask_dev ? T_prefix : 0;
+  a.scratch = static_cast<float*>(scratch_dev); a.scratch_bytes = scratch_bytes;
+  if (impl == 2) return launch_attn_tma(dtype, a, (cudaStream_t)stream);
+  if (impl == 0 && dtype == VLG_BF16) return launch_attn_tma(dtype, a, (cudaStream_t)stream);
+  return launch_attn_generic(dtype, a, (cudaStream_t)stream);
+}
+
+extern "C" size_t vlg_attn_scratch_bytes(int rows, int H, int D, int S_max) { return attn_scratch_bytes(rows, H, D, S_max); }

@@ -1,0 +1,281 @@
+// Single-query attention over the bf16 KV-cache prefix [0, pos] -- the bandwidth kernel of the decode step
+// (84 % of the algorithmic bytes at batch-64 CFG).
+//
+// HBM-bound streaming work: every K/V byte of the valid prefix is read exactly once per step and used for
+// one FMA, so the design goal is bytes in flight, not flops:
+//   * persistent CTAs (one per SM), work items = (row, head[, sequence split]) dealt round-robin;
+//   * warp 0 is a TMA producer: it streams 32-position K and V tiles (4 KB each, 128-byte swizzle) through a
+//     24-stage shared-memory ring (192 KB in flight per SM) and runs ahead ACROSS work items, so the pipe
+//     never drains between the short (<= 19-tile) sequences of one step;
+//   * 8 consumer warps each own every 8th tile: one lane per cache position for q.k (the swizzle makes the
+//     16-byte row reads conflict-free), warp-level online softmax in the exp2 domain, then 8 lanes per
+//     position for p.V; per-warp partial (m, l, o) states are merged through shared memory once per item.
+// Numerics: fp32 throughout, single rounding of the output to bf16 (torch math SDPA);
+// the softmax scale is folded into q (1/sqrt(D) is a power of two for D = 64) together with log2(e).
+#include "common.cuh"
+#include "kernels.h"
+
+namespace vlg {
+
+constexpr int kTile = 32;                   // cache positions per TMA tile
+constexpr int kCW = 8;                      // consumer warps
+constexpr int kStagesA = 24;                // ring depth (multiple of kCW: stage s always belongs to warp s % kCW)
+constexpr int kTileBytes = kTile * 128;     // one K or V tile (D = 64 bf16 = 128 B per position)
+constexpr int kStageBytesA = 2 * kTileBytes;
+constexpr int kAttnTmaThreads = (kCW + 1) * 32;
+constexpr int kMaxSplitsT = 32;
+
+struct ItemSlot { float m, l, pad0, pad1; float o[64]; };
+
+struct AttnTmaSmem {
+  uint8_t ring[kStagesA][kStageBytesA];     // 1024-byte aligned (swizzle atom = 8 rows x 128 B)
+  ItemSlot slot[2][kCW];
+  float p[kCW][kTile];
+  uint64_t full[kStagesA], empty[kStagesA];
+};
+
+__device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, %0;" ::"n"(kCW * 32) : "memory"); }
+
+__global__ void __launch_bounds__(kAttnTmaThreads, 1)
+attn_decode_tma_kernel(const __grid_constant__ TensorMap tmK, const __grid_constant__ TensorMap tmV,
+                       const __nv_bfloat16* __restrict__ q, __nv_bfloat16* __restrict__ out, float* __restrict__ part,
+                       int n_rh, int H, int S_max, const int* pos_ptr, int pos_imm,
+                       const uint8_t* __restrict__ mask, int T_prefix, int n_splits) {
+  extern __shared__ uint8_t smem_raw[];
+  AttnTmaSmem& sm = *reinterpret_cast<AttnTmaSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    for (int s = 0; s < kStagesA; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], 1); }
+    fence_mbar_init();
+  }
+  __syncthreads();
+
+  const int pos = pos_ptr ? *pos_ptr : pos_imm;
+  const int n = pos + 1;
+  int chunk = (n + n_splits - 1) / n_splits;
+  chunk = (chunk + kTile - 1) / kTile * kTile;
+  const int n_items = n_rh * n_splits;
+
+  if (warp == kCW) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      uint32_t gt = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int rh = item / n_splits, split = item - rh * n_splits;
+        const int s_begin = split * chunk, s_end = min(n, s_begin + chunk);
+        const int n_tiles = s_end > s_begin ? (s_end - s_begin + kTile - 1) / kTile : 0;
+        const int row0 = rh * S_max + s_begin;
+        for (int t = 0; t < n_tiles; ++t, ++gt) {
+          const uint32_t st = gt % kStagesA, it = gt / kStagesA;
+          mbar_wait(&sm.empty[st], (it & 1) ^ 1);
+          mbar_expect_tx(&sm.full[st], kStageBytesA);
+          tma_load_2d_hint(sm.ring[st], &tmK, &sm.full[st], 0, row0 + t * kTile, kEvictFirst);
+          tma_load_2d_hint(sm.ring[st] + kTileBytes, &tmV, &sm.full[st], 0, row0 + t * kTile, kEvictFirst);
+        }
+      }
+    }
+    return;
+  }
+
+  // -------------------------------------------------------------------- consumers
+  const int g = lane >> 3, c = lane & 7;
+  const float kScale = 0.125f * 1.4426950408889634f;   // 1/sqrt(64) * log2(e)
+  uint32_t gt0 = 0;                                     // tiles issued before the current item
+  int item_i = 0;
+  uint4 qraw[8];
+  if (blockIdx.x < n_items) {
+    const uint4* qp = reinterpret_cast<const uint4*>(q + (size_t)(blockIdx.x / n_splits) * 64);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) qraw[i] = qp[i];
+  }
+  for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++item_i) {
+    const int rh = item / n_splits, split = item - rh * n_splits;
+    const int s_begin = split * chunk, s_end = min(n, s_begin + chunk);
+    const int n_tiles = s_end > s_begin ? (s_end - s_begin + kTile - 1) / kTile : 0;
+    const uint8_t* mrow = mask ? mask + (size_t)(rh / H) * T_prefix : nullptr;
+
+    float qf[64];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      qf[8 * i + 0] = bf16lo(qraw[i].x) * kScale; qf[8 * i + 1] = bf16hi(qraw[i].x) * kScale;
+      qf[8 * i + 2] = bf16lo(qraw[i].y) * kScale; qf[8 * i + 3] = bf16hi(qraw[i].y) * kScale;
+      qf[8 * i + 4] = bf16lo(qraw[i].z) * kScale; qf[8 * i + 5] = bf16hi(qraw[i].z) * kScale;
+      qf[8 * i + 6] = bf16lo(qraw[i].w) * kScale; qf[8 * i + 7] = bf16hi(qraw[i].w) * kScale;
+    }
+    {  // prefetch the next item's query while this item's tiles are processed
+      const int nxt = item + gridDim.x;
+      if (nxt < n_items) {
+        const uint4* qp = reinterpret_cast<const uint4*>(q + (size_t)(nxt / n_splits) * 64);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) qraw[i] = qp[i];
+      }
+    }
+
+    float m = -INFINITY, l = 0.f, acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+
+    // first tile of this item owned by this warp: (gt0 + t) % kCW == warp
+    int t = (warp - (int)(gt0 % kCW) + kCW) % kCW;
+    for (; t < n_tiles; t += kCW) {
+      const uint32_t gt = gt0 + t, st = gt % kStagesA, it = gt / kStagesA;
+      mbar_wait(&sm.full[st], it & 1);
+      const uint8_t* kt = sm.ring[st];
+      const uint8_t* vt = kt + kTileBytes;
+      const int sidx = s_begin + t * kTile + lane;     // this lane's cache position
+
+      // ---- scores: lane <-> position, 4 independent partial sums
+      float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
+#pragma unroll
+      for (int ch = 0; ch < 8; ++ch) {
+        const uint4 kk = *reinterpret_cast<const uint4*>(kt + lane * 128 + ((ch ^ (lane & 7)) << 4));
+        d0 = fmaf(qf[8 * ch + 0], bf16lo(kk.x), d0); d1 = fmaf(qf[8 * ch + 1], bf16hi(kk.x), d1);
+        d2 = fmaf(qf[8 * ch + 2], bf16lo(kk.y), d2); d3 = fmaf(qf[8 * ch + 3], bf16hi(kk.y), d3);
+        d0 = fmaf(qf[8 * ch + 4], bf16lo(kk.z), d0); d1 = fmaf(qf[8 * ch + 5], bf16hi(kk.z), d1);
+        d2 = fmaf(qf[8 * ch + 6], bf16lo(kk.w), d2); d3 = fmaf(qf[8 * ch + 7], bf16hi(kk.w), d3);
+      }
+      float sc = (d0 + d1) + (d2 + d3);
+      bool vis = sidx < s_end;
+      if (mrow != nullptr && sidx < T_prefix) vis = vis && (sidx == pos || mrow[sidx] != 0);
+      sc = vis ? sc : -INFINITY;
+
+      // ---- online softmax (log2 domain)
+      const float m_new = fmaxf(m, warp_max(sc));
+      if (m_new == -INFINITY) {                         // whole tile masked and nothing seen yet
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm.empty[st]);
+        continue;
+      }
+      const float corr = exp2f(m - m_new);
+      const float p = exp2f(sc - m_new);
+      m = m_new;
+      l = fmaf(l, corr, p);                             // per-lane partial of the row sum
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] *= corr;
+      __syncwarp();                                     // previous tile's readers of sm.p are done
+      sm.p[warp][lane] = p;
+      __syncwarp();
+
+      // ---- o += p . V : lane (g, c) covers rows 8g..8g+7, dims 8c..8c+7
+      const float4 pa = *reinterpret_cast<const float4*>(&sm.p[warp][8 * g]);
+      const float4 pb = *reinterpret_cast<const float4*>(&sm.p[warp][8 * g + 4]);
+      const float pj[8] = {pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, pb.w};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int row = 8 * g + j;
+        if (pj[j] != 0.f) {                             // skips masked / beyond-the-end rows (their bytes may be stale)
+          const uint4 vv = *reinterpret_cast<const uint4*>(vt + row * 128 + ((c ^ (row & 7)) << 4));
+          acc[0] = fmaf(pj[j], bf16lo(vv.x), acc[0]); acc[1] = fmaf(pj[j], bf16hi(vv.x), acc[1]);
+          acc[2] = fmaf(pj[j], bf16lo(vv.y), acc[2]); acc[3] = fmaf(pj[j], bf16hi(vv.y), acc[3]);
+          acc[4] = fmaf(pj[j], bf16lo(vv.z), acc[4]); acc[5] = fmaf(pj[j], bf16hi(vv.z), acc[5]);
+          acc[6] = fmaf(pj[j], bf16lo(vv.w), acc[6]); acc[7] = fmaf(pj[j], bf16hi(vv.w), acc[7]);
+        }
+      }
+      __syncwarp();                                     // all lanes finished reading the stage
+      if (lane == 0) mbar_arrive(&sm.empty[st]);
+    }
+    gt0 += n_tiles;
+
+    // ---- fold the 4 row groups of the warp, publish the warp's partial state
+    l = warp_sum(l);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 8);
+      acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 16);
+    }
+    ItemSlot& mine = sm.slot[item_i & 1][warp];
+    if (lane == 0) { mine.m = m; mine.l = l; }
+    if (lane < 8) {
+      *reinterpret_cast<float4*>(&mine.o[8 * c]) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+      *reinterpret_cast<float4*>(&mine.o[8 * c + 4]) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+    }
+    consumer_bar();
+    if (warp == item_i % kCW) {                         // merge duty rotates over the consumer warps
+      const ItemSlot* sl = sm.slot[item_i & 1];
+      float mm = -INFINITY;
+#pragma unroll
+      for (int w = 0; w < kCW; ++w) mm = fmaxf(mm, sl[w].m);
+      float lt = 0.f, o0 = 0.f, o1 = 0.f;
+#pragma unroll
+      for (int w = 0; w < kCW; ++w) {
+        const float a = sl[w].m == -INFINITY ? 0.f : exp2f(sl[w].m - mm);
+        lt = fmaf(sl[w].l, a, lt);
+        const float2 ov = *reinterpret_cast<const float2*>(&sl[w].o[2 * lane]);
+        o0 = fmaf(ov.x, a, o0);
+        o1 = fmaf(ov.y, a, o1);
+      }
+      if (n_splits == 1) {
+        const float inv = 1.0f / lt;
+        *reinterpret_cast<uint32_t*>(out + (size_t)rh * 64 + 2 * lane) = pack_bf16(o0 * inv, o1 * inv);
+      } else {
+        float* pp = part + ((size_t)rh * n_splits + split) * 66;
+        *reinterpret_cast<float2*>(pp + 2 + 2 * lane) = make_float2(o0, o1);
+        if (lane == 0) { pp[0] = mm * 0.6931471805599453f; pp[1] = lt; }   // natural-log units for the combiner
+      }
+    }
+  }
+}
+
+// folds the split partials (same layout as the generic kernel's): out = sum_s o_s e^{m_s - M} / sum_s l_s e^{m_s - M}
+__global__ void attn_tma_combine_kernel(const float* __restrict__ part, __nv_bfloat16* __restrict__ out, int n_splits) {
+  const int rh = blockIdx.x, d = threadIdx.x;
+  const float* pp = part + (size_t)rh * n_splits * 66;
+  float mm = -INFINITY;
+  for (int s = 0; s < n_splits; ++s) mm = fmaxf(mm, pp[s * 66]);
+  float lt = 0.f, o = 0.f;
+  for (int s = 0; s < n_splits; ++s) {
+    const float ms = pp[s * 66];
+    const float a = (ms == -INFINITY) ? 0.f : expf(ms - mm);
+    lt += pp[s * 66 + 1] * a;
+    o += pp[s * 66 + 2 + d] * a;
+  }
+  out[(size_t)rh * 64 + d] = __float2bfloat16_rn(o / lt);
+}
+
+int launch_attn_tma(int dtype, const AttnArgs& a, cudaStream_t st) {
+  VLG_REQUIRE(dtype == VLG_BF16, "attn(tma): bf16 only");
+  VLG_REQUIRE(a.D == 64, "attn(tma): head_dim %d not supported (64)", a.D);
+  VLG_REQUIRE(a.rows > 0 && a.H > 0 && a.S_max > 0, "attn(tma): bad shape");
+  const int n_rh = a.rows * a.H;
+  const uint64_t total_rows = (uint64_t)n_rh * a.S_max;
+  VLG_REQUIRE(total_rows < (1ull << 31), "attn(tma): cache too large for 32-bit TMA coordinates");
+  TensorMap tmK, tmV;
+  int rc = make_tmap_bf16_2d(&tmK, a.k_cache, total_rows, 64, 128, kTile, 64, true);
+  if (rc) return rc;
+  if ((rc = make_tmap_bf16_2d(&tmV, a.v_cache, total_rows, 64, 128, kTile, 64, true))) return rc;
+
+  // sequence splits only when (row, head) pairs alone cannot occupy the SMs
+  const int sms = num_sms();
+  int n_splits = 1;
+  if (n_rh < 2 * sms) {
+    int want = (2 * sms + n_rh - 1) / n_rh, by_len = (a.max_pos + 1 + 2 * kTile - 1) / (2 * kTile);
+    n_splits = want < by_len ? want : by_len;
+    if (n_splits < 1) n_splits = 1;
+    if (n_splits > kMaxSplitsT) n_splits = kMaxSplitsT;
+  }
+  if (n_splits > 1)
+    VLG_REQUIRE(a.scratch && a.scratch_bytes >= (size_t)n_rh * n_splits * 66 * sizeof(float),
+                "attn(tma): scratch too small for %d splits", n_splits);
+  const int smem = (int)sizeof(AttnTmaSmem) + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    VLG_CUDA(cudaFuncSetAttribute(attn_decode_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
+  const int n_items = n_rh * n_splits;
+  const int grid = n_items < sms ? n_items : sms;
+  attn_decode_tma_kernel<<<grid, kAttnTmaThreads, smem, st>>>(
+      tmK, tmV, (const __nv_bfloat16*)a.q, (__nv_bfloat16*)a.out, a.scratch, n_rh, a.H, a.S_max, a.pos_ptr, a.pos_imm,
+      a.prefix_mask, a.T_prefix, n_splits);
+  VLG_LAUNCH_CHECK();
+  if (n_splits > 1) {
+    attn_tma_combine_kernel<<<n_rh, 64, 0, st>>>(a.scratch, (__nv_bfloat16*)a.out, n_splits);
+    VLG_LAUNCH_CHECK();
+  }
+  return VLG_OK;
+}
+
+}  // namespace vlg

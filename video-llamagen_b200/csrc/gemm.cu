@@ -1,0 +1,228 @@
+// out[rows, N] = x[rows, K] . w[N, K]^T (nn.Linear without bias) with fused epilogues (epilogue.cuh).
+//
+//  * bf16: tcgen05 tensor cores.  One CTA owns a [128 x BN] output tile: rows ride the 128 TMEM lanes
+//    (TMA zero-fills rows >= `rows`), BN weight rows are the N operand.  K is streamed through an
+//    8-stage TMA ring (A = activations 128x64, B = weights BNx64, both K-major, 128B swizzle); one
+//    elected thread issues tcgen05.mma (M=128, N=BN, K=16) with the fp32 accumulator in TMEM; four
+//    epilogue warps read it back with tcgen05.ld (lane == output row) and apply the epilogue.
+//    The decode GEMMs are weight-streaming bound (M <= 256): BN is small so that N/BN CTAs spread the
+//    weight stream over the SMs; activations are re-read from L2 (evict-last), weights evict-first.
+//  * fp32: CUDA-core FMA only (no TF32), fixed summation order -- the exact path behind the greedy
+//    bit-exact contract.  One warp owns 8 output columns, lanes split K, 8 rows per pass.
+#include "common.cuh"
+#include "epilogue.cuh"
+
+namespace vlg {
+
+// ============================================================================ tcgen05 bf16 GEMM
+constexpr int kGemmThreads = 192;  // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
+constexpr int kBM = 128;
+constexpr int kBK = 64;            // 64 bf16 = one 128-byte swizzle row
+
+template <int BN> struct GemmCfg {
+  static constexpr int kABytes = kBM * kBK * 2;
+  static constexpr int kBBytes = (BN * kBK * 2 + 1023) / 1024 * 1024;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = (BN <= 64) ? 8 : 6;
+  static constexpr int kTmemCols = BN < 32 ? 32 : BN;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int BN, int EPI>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_bf16_tc_kernel(const __grid_constant__ TensorMap tmA, const __grid_constant__ TensorMap tmB, int rows, int K,
+                    EpiParams P) {
+  using Cfg = GemmCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint64_t* empty = full + Cfg::kStages;
+  uint64_t* acc_ready = empty + Cfg::kStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_ready + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * BN, m0 = blockIdx.y * kBM;
+  const int nkb = K / kBK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(acc_ready, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_acc = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % Cfg::kStages, it = kb / Cfg::kStages;
+        mbar_wait(&empty[s], (it & 1) ^ 1);
+        uint8_t* a = smem + s * Cfg::kStageBytes;
+        mbar_expect_tx(&full[s], kBM * kBK * 2 + BN * kBK * 2);
+        tma_load_2d_hint(a, &tmA, &full[s], kb * kBK, m0, kEvictLast);
+        tma_load_2d_hint(a + Cfg::kABytes, &tmB, &full[s], kb * kBK, n0, kEvictFirst);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(kBM, BN);
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % Cfg::kStages, it = kb / Cfg::kStages;
+        mbar_wait(&full[s], it & 1);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem + s * Cfg::kStageBytes);
+        const uint64_t adesc = umma_desc_sw128(a_addr), bdesc = umma_desc_sw128(a_addr + Cfg::kABytes);
+#pragma unroll
+        for (int k = 0; k < kBK / 16; ++k)  // +32 bytes along K inside the swizzle row = +2 in the address field
+          umma_bf16(tmem_acc, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+        umma_commit(&empty[s]);             // frees the smem stage once these MMAs retire
+      }
+      umma_commit(acc_ready);
+    }
+  } else {
+    const int quad = warp & 3;              // TMEM lanes [32*quad, 32*quad+32) are the ones this warp may read
+    const int r = m0 + quad * 32 + lane;
+    mbar_wait(acc_ready, 0);
+    tc_fence_after();
+#pragma unroll
+    for (int c = 0; c < BN; c += 16) {
+      float v[16];
+      tmem_ld16(tmem_acc + (static_cast<uint32_t>(quad * 32) << 16) + c, v);
+      if (r < rows) {
+        epi8<EPI, __nv_bfloat16>(r, n0 + c, v, P);
+        epi8<EPI, __nv_bfloat16>(r, n0 + c + 8, v + 8, P);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<Cfg::kTmemCols>(tmem_acc);
+}
+
+template <int BN, int EPI>
+static int launch_tc(const void* x, const void* w, int rows, int N, int K, const EpiParams& P, cudaStream_t st) {
+  using Cfg = GemmCfg<BN>;
+  TensorMap tmA, tmB;
+  int rc = make_tmap_bf16_2d(&tmA, x, (uint64_t)rows, (uint64_t)K, (uint64_t)K * 2, kBM, kBK, true);
+  if (rc) return rc;
+  rc = make_tmap_bf16_2d(&tmB, w, (uint64_t)N, (uint64_t)K, (uint64_t)K * 2, BN, kBK, true);
+  if (rc) return rc;
+  auto kern = gemm_bf16_tc_kernel<BN, EPI>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    VLG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  dim3 grid(N / BN, (rows + kBM - 1) / kBM);
+  kern<<<grid, kGemmThreads, Cfg::kSmemBytes, st>>>(tmA, tmB, rows, K, P);
+  VLG_LAUNCH_CHECK();
+  return VLG_OK;
+}
+
+// ============================================================================ exact fp32 GEMM
+constexpr int kF32Warps = 4;
+
+template <int EPI>
+__global__ void __launch_bounds__(kF32Warps * 32)
+gemm_f32_kernel(const float* __restrict__ x, const float* __restrict__ w, int rows, int N, int K, EpiParams P) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = (blockIdx.x * kF32Warps + warp) * 8;
+  if (n0 >= N) return;
+  for (int r0 = 0; r0 < rows; r0 += 8) {
+    float acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+    for (int k = lane * 4; k < K; k += 128) {
+      float4 wv[8], xv[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) wv[j] = *reinterpret_cast<const float4*>(w + (size_t)(n0 + j) * K + k);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        int r = min(r0 + i, rows - 1);
+        xv[i] = *reinterpret_cast<const float4*>(x + (size_t)r * K + k);
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float a = acc[i][j];
+          a = __fmaf_rn(xv[i].x, wv[j].x, a);
+          a = __fmaf_rn(xv[i].y, wv[j].y, a);
+          a = __fmaf_rn(xv[i].z, wv[j].z, a);
+          a = __fmaf_rn(xv[i].w, wv[j].w, a);
+          acc[i][j] = a;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[i][j] = warp_sum(acc[i][j]);
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (lane == i && r0 + i < rows) epi8<EPI, float>(r0 + i, n0, acc[i], P);
+  }
+}
+
+template <int EPI>
+static int launch_f32(const void* x, const void* w, int rows, int N, int K, const EpiParams& P, cudaStream_t st) {
+  int groups = N / 8;
+  gemm_f32_kernel<EPI><<<(groups + kF32Warps - 1) / kF32Warps, kF32Warps * 32, 0, st>>>(
+      static_cast<const float*>(x), static_cast<const float*>(w), rows, N, K, P);
+  VLG_LAUNCH_CHECK();
+  return VLG_OK;
+}
+
+// ============================================================================ dispatch
+// Tile width per problem: enough CTAs to pull the weight stream with all SMs, as few as possible
+// beyond that (every CTA re-reads the whole activation matrix from L2).
+template <int EPI>
+static int launch_tc_auto(const void* x, const void* w, int rows, int N, int K, const EpiParams& P, cudaStream_t st) {
+  if (N % 32 == 0 && N / 32 >= 96) return launch_tc<32, EPI>(x, w, rows, N, K, P, st);
+  return launch_tc<16, EPI>(x, w, rows, N, K, P, st);
+}
+
+int launch_gemm(int dtype, int epi, const void* x, const void* w, int rows, int N, int K, const EpiParams& P,
+                cudaStream_t st) {
+  VLG_REQUIRE(rows > 0 && N > 0 && K > 0, "gemm: bad shape rows=%d N=%d K=%d", rows, N, K);
+  if (dtype == VLG_BF16) {
+    VLG_REQUIRE(K % kBK == 0 && N % 16 == 0, "gemm(bf16): need K %% 64 == 0 and N %% 16 == 0 (K=%d N=%d)", K, N);
+    switch (epi) {
+      case EPI_STORE: return launch_tc_auto<EPI_STORE>(x, w, rows, N, K, P, st);
+      case EPI_STORE_F32: return launch_tc_auto<EPI_STORE_F32>(x, w, rows, N, K, P, st);
+      case EPI_RESID: return launch_tc_auto<EPI_RESID>(x, w, rows, N, K, P, st);
+      case EPI_SWIGLU: return launch_tc_auto<EPI_SWIGLU>(x, w, rows, N, K, P, st);
+      case EPI_QKV_ROPE: return launch_tc_auto<EPI_QKV_ROPE>(x, w, rows, N, K, P, st);
+      case EPI_GELU: return launch_tc_auto<EPI_GELU>(x, w, rows, N, K, P, st);
+    }
+  } else if (dtype == VLG_F32) {
+    VLG_REQUIRE(K % 4 == 0 && N % 8 == 0, "gemm(fp32): need K %% 4 == 0 and N %% 8 == 0 (K=%d N=%d)", K, N);
+    switch (epi) {
+      case EPI_STORE: case EPI_STORE_F32: return launch_f32<EPI_STORE>(x, w, rows, N, K, P, st);
+      case EPI_RESID: return launch_f32<EPI_RESID>(x, w, rows, N, K, P, st);
+      case EPI_SWIGLU: return launch_f32<EPI_SWIGLU>(x, w, rows, N, K, P, st);
+      case EPI_QKV_ROPE: return launch_f32<EPI_QKV_ROPE>(x, w, rows, N, K, P, st);
+      case EPI_GELU: return launch_f32<EPI_GELU>(x, w, rows, N, K, P, st);
+    }
+  }
+  set_error("gemm: unsupported dtype %d / epilogue %d", dtype, epi);
+  return VLG_ERR_ARG;
+}
+
+}  // namespace vlg
+
+extern "C" int vlg_linear(const void* x_dev, const void* w_dev, void* out_dev, int rows, int N, int K, int dtype,
+                          int out_f32, void* stream) {
+  using namespace vlg;
+  VLG_REQUIRE(x_dev && w_dev && out_dev, "vlg_linear: null pointer");
+  EpiParams P{};
+  P.out = out_dev;
+  P.ld_out = N;
+  return launch_gemm(dtype, out_f32 ? EPI_STORE_F32 : EPI_STORE, x_dev, w_dev, rows, N, K, P, (cudaStream_t)stream);
+}

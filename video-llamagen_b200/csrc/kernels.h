@@ -1,0 +1,56 @@
+// Internal launcher declarations shared between the .cu translation units.
+#pragma once
+#include "common.cuh"
+#include "epilogue.cuh"
+
+namespace vlg {
+
+int launch_rmsnorm(int dtype, const void* x, const void* w, void* out, int rows, int dim, float eps, cudaStream_t st);
+
+int launch_gather(int dtype, const void* table, void* out, int rows, int dim, const int64_t* idx64,
+                  const int32_t* seq, int seq_stride, const int* col_ptr, int col_off, const int64_t* labels, int B,
+                  int null_class, int table_rows, cudaStream_t st);
+
+int launch_gemm(int dtype, int epi, const void* x, const void* w, int rows, int N, int K, const EpiParams& P,
+                cudaStream_t st);
+
+// Single-position attention over the cache prefix.  pos comes from *pos_ptr when non-null.
+struct AttnArgs {
+  const void* q;        // [rows, H, D]
+  const void* k_cache;  // [rows, H, S_max, D]
+  const void* v_cache;
+  void* out;            // [rows, H*D]
+  int rows, H, D, S_max;
+  const int* pos_ptr;
+  int pos_imm;
+  const uint8_t* prefix_mask;  // [rows, T_prefix] or null
+  int T_prefix;
+  float* scratch;       // split partials
+  size_t scratch_bytes;
+  int max_pos;          // upper bound of pos over the life of a captured graph (sizes the split count)
+};
+int launch_attn_generic(int dtype, const AttnArgs& a, cudaStream_t st);
+size_t attn_scratch_bytes(int rows, int H, int D, int S_max);
+// bf16 only: persistent, TMA-fed streaming kernel (attn_tma.cu)
+int launch_attn_tma(int dtype, const AttnArgs& a, cudaStream_t st);
+
+// Fused CFG mix + temperature + top-k/top-p + softmax + pick.
+struct SampleArgs {
+  const float* logits;  // [rows, V]
+  int rows, B, V;
+  vlg_sample_params p;
+  const float* noise;   // [B, V] or null
+  int64_t* idx_out;     // [B] or null
+  float* probs_out;     // [B, V] or null
+  float* filtered_out;  // [B, V] or null: logits after temperature and top-k/top-p (-inf where removed)
+  // decode-loop extras (all optional)
+  int32_t* seq_out;     // [B, seq_stride]: token written at column *step_ptr
+  int seq_stride;
+  int* step_ptr;        // device step counter: read for the column / RNG offset / cfg_interval, then incremented
+  int* pos_ptr;         // device cache position: incremented together with the step
+  int cfg_interval;     // -1: always guided
+  unsigned* done_ctr;   // block-completion counter for the increment
+};
+int launch_sample(const SampleArgs& a, cudaStream_t st);
+
+}  // namespace vlg
