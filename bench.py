@@ -1,0 +1,315 @@
+#!/usr/bin/env python
+"""bench.py -- generated visual tokens/sec of the decode hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Workload (config.workload): BASELINE cfg-2 -- GPT-L c2i 384 px (24x24 = 576 tokens), bf16, batch 64 with CFG 4.0
+(128 cache rows), top-k 2000, temperature 1.0, random-init weights, synthetic class labels.  One "step" is one
+full generate() over one batch: prefill + 575 graph-replayed decode steps.
+
+  value       tokens/s with the class labels already resident in HBM (vlg_generate), CUDA events, max over ranks
+  e2e         same through the host-buffer C-ABI call (vlg_generate_c2i_host): pinned labels H2D + tokens D2H inside
+  roofline    the dominant kernel (KV-cache attention): algorithmic K/V bytes per launch / its measured duration
+  cpu_baseline  the oracle port (reference algorithm restated, oracle/ar_decode.py) on this host's cores, bounded sample
+
+N > 1 (torchrun, one rank per GPU): every rank decodes its own 64-sample shard of a 64*N global batch (weak scaling),
+no collective inside the loop, one NCCL all_gather of the int32 code indices per step inside the timed region.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "video-llamagen_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+MODEL, BLOCK, B_LOCAL, NEW_TOKENS = "GPT-L", 576, 64, 576
+CFG_SCALE, TOP_K, TOP_P, TEMP = 4.0, 2000, 1.0, 1.0
+METRIC = "generated visual tokens/sec, GPT-L c2i-384 CFG decode"
+UNIT = "tokens/s"
+
+
+def workload_config(n_gpus):
+    return {"workload": "cfg-2: GPT-L c2i 384px (24x24=576 tokens) bf16, batch 64 with CFG 4.0 (128 rows), top-k 2000",
+            "per_gpu_batch": B_LOCAL, "global_batch": B_LOCAL * n_gpus, "new_tokens": NEW_TOKENS,
+            "parallelism": f"sample-sharded dp{n_gpus}, all_gather of code indices",
+            "l2": "inputs larger than L2 (7.3 GB KV cache + 0.65 GB weights streamed per step; no flush needed)"}
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        return json.load(open(path)), "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
+
+
+# --------------------------------------------------------------------------- clocks sampler
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 7 for n, v in zip(names, r[3:7]) if v.lower().startswith("active")})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------- algorithmic bytes
+def algorithmic_bytes_generate(cfg, rows, T, N, V):
+    d, L, hid = cfg.dim, cfg.n_layer, cfg.hidden_dim
+    W = (L * (4 * d * d + 3 * d * hid) + V * d) * 2
+    total = 0
+    for p in range(T - 1, T + N - 1):                 # position of the input token of each of the N forward passes
+        total += W + rows * 2 * d * 2 * L * (p + 1) + rows * 2 * d * 2 * L + rows * V * 4 * 2
+    return total
+
+
+def attention_kernel_roofline(dev, rows, H, S_max, n_pos, peak_gbs, src):
+    """Time the attention kernel alone (CUDA events on its stream) over the position mix of one generate():
+    launches at pos = 0..n_pos-1, cycling over several distinct cache regions so no launch finds its K/V in L2."""
+    import torch
+    from vlg import _lib as L
+    D = 64
+    regions = 6                                            # 6 x 306 MB of K+V >> 126 MB of L2
+    g = torch.Generator(device=dev).manual_seed(0)
+    q = torch.randn(rows, H, D, device=dev, generator=g).bfloat16()
+    ks = [torch.randn(rows, H, S_max, D, device=dev, generator=g).bfloat16() for _ in range(regions)]
+    vs = [torch.randn(rows, H, S_max, D, device=dev, generator=g).bfloat16() for _ in range(regions)]
+    out = torch.empty(rows, H * D, device=dev, dtype=torch.bfloat16)
+    lib = L.lib()
+    st = torch.cuda.Stream(device=dev)
+    positions = list(range(0, n_pos))
+    with torch.cuda.stream(st):
+        for p in (0, n_pos // 2, n_pos - 1):               # warm-up
+            L.check(lib.vlg_attn_decode(L.ptr(q), L.ptr(ks[0]), L.ptr(vs[0]), L.ptr(out), rows, H, D, S_max, p, None, 0,
+                                        L.VLG_BF16, 2, None, 0, L.stream()))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        st.synchronize()
+        e0.record(st)
+        for i, p in enumerate(positions):
+            r = i % regions
+            L.check(lib.vlg_attn_decode(L.ptr(q), L.ptr(ks[r]), L.ptr(vs[r]), L.ptr(out), rows, H, D, S_max, p, None, 0,
+                                        L.VLG_BF16, 2, None, 0, L.stream()))
+        e1.record(st)
+        st.synchronize()
+    ms = e0.elapsed_time(e1)
+    bytes_total = sum(rows * H * (p + 1) * D * 2 * 2 + rows * H * D * 2 * 2 for p in positions)   # K,V prefix + q + out
+    achieved = bytes_total / (ms * 1e-3) / 1e9
+    return {"bound": "hbm", "kernel": "attn_decode_tma_kernel", "achieved": round(achieved, 1), "peak": peak_gbs,
+            "unit": "GB/s", "frac": round(achieved / peak_gbs, 4), "traffic": None, "peak_source": src,
+            "launches_timed": len(positions), "avg_launch_us": round(ms * 1e3 / len(positions), 2),
+            "algorithmic_bytes_per_launch_avg": bytes_total // len(positions)}
+
+
+# --------------------------------------------------------------------------- CPU reference arm (oracle port)
+def cpu_reference_sample(decode_steps, threads=None):
+    """Reference algorithm (oracle/ar_decode.py restatement of generate.py + gpt.py) on the host cores: cfg-2 rows and
+    geometry, fp32 on CPU, prefill + `decode_steps` decode steps.  Its per-step cost is position-independent because the
+    reference attends over all S_max slots and copies both caches every layer (gpt.py:230-237)."""
+    import torch
+    from oracle import ar_decode as O
+    threads = threads or os.cpu_count()
+    torch.set_num_threads(threads)
+    geo = O.Geometry(block_size=BLOCK, **O.NAMED[MODEL])
+    w = O.init_weights(geo, seed=0)
+    cond = torch.randint(0, 1000, (B_LOCAL,), generator=torch.Generator().manual_seed(1234))
+    n = decode_steps + 1
+    # generate() allocates caches for the full 576-token sequence (as the reference does); run only n tokens of it
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        rows = torch.cat([cond, torch.ones_like(cond) * geo.num_classes])
+        st = O.DecodeState(geo, 2 * B_LOCAL, 1 + NEW_TOKENS, torch.float32)
+        t_alloc = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        logits = O.forward_logits(geo, w, st, cond=rows, input_pos=torch.arange(1))
+        tok = O.sample(O.cfg_mix(logits, CFG_SCALE), temperature=TEMP, top_k=TOP_K, top_p=TOP_P)[0]
+        for i in range(decode_steps):
+            logits = O.forward_logits(geo, w, st, idx=torch.cat([tok, tok]).view(-1, 1), input_pos=torch.tensor([1 + i]))
+            tok = O.sample(O.cfg_mix(logits, CFG_SCALE), temperature=TEMP, top_k=TOP_K, top_p=TOP_P)[0]
+    dt = time.perf_counter() - t0
+    return {"value": round(B_LOCAL * n / dt, 2), "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"cfg-2 rows on CPU fp32: prefill + {decode_steps} decode steps of the 576 "
+                      f"({dt:.1f} s; cache alloc {t_alloc:.1f} s excluded), per-step cost position-independent"}, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    times, last = [], None
+    for i in range(args.warmup + args.steps):
+        last, dt = cpu_reference_sample(args.ref_decode_steps)
+        if i >= args.warmup:
+            times.append(dt)
+    tok = B_LOCAL * (args.ref_decode_steps + 1)
+    value = tok / statistics.mean(times)
+    last["value"] = round(value, 2)
+    line = {"impl": "reference", "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(statistics.mean(times) * 1e3, 1),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args.gpus), "cpu_baseline": last,
+            "e2e": {"value": round(value, 2), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------- GPU arm
+def run_vlg(args):
+    import torch
+    import torch.distributed as dist
+    from vlg import _lib as L
+    from vlg.gpt import GPT_models
+    from vlg.generate import generate
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the vlg path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun --nproc-per-node {args.gpus}"
+
+    torch.manual_seed(0)
+    model = GPT_models[MODEL](block_size=BLOCK, cls_token_num=1, model_type="c2i").eval()
+    torch.nn.init.normal_(model.output.weight, std=0.02)      # zero-initialised in the reference (gpt.py:307)
+    model = model.to(dev, torch.bfloat16)
+    gen = torch.Generator().manual_seed(1234)
+    cond_all = torch.randint(0, 1000, (B_LOCAL * world,), generator=gen)
+    cond_host = cond_all[rank * B_LOCAL:(rank + 1) * B_LOCAL].contiguous().pin_memory()
+    cond_dev = cond_host.to(dev)
+    tokens_host = torch.empty(B_LOCAL, NEW_TOKENS, dtype=torch.int32).pin_memory()
+    gathered = torch.empty(world * B_LOCAL, NEW_TOKENS, dtype=torch.int32, device=dev) if world > 1 else None
+    kw = dict(cfg_scale=CFG_SCALE, temperature=TEMP, top_k=TOP_K, top_p=TOP_P, sample_logits=True)
+    stream = torch.cuda.Stream(device=dev)
+    lib = L.lib()
+
+    def one_step(seed):
+        toks = generate(model, cond_dev, NEW_TOKENS, seed=1000 * seed + rank, **kw)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, toks)
+        return toks
+
+    def fence():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, n):
+        fence()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for i in range(n):
+            fn(i)
+        e1.record(stream)
+        fence()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    with torch.cuda.stream(stream):
+        for i in range(args.warmup):
+            toks = one_step(100 + i)
+        torch.cuda.synchronize()
+        assert int(toks.min()) >= 0 and int(toks.max()) < 16384
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+        launches0 = lib.vlg_launch_count()
+        ms = timed(one_step, args.steps)
+        launches = lib.vlg_launch_count() - launches0
+
+        # e2e: host labels -> host tokens through the C-ABI call (copies + sync inside)
+        eng = model._engine
+
+        def e2e_step(i):
+            eng.generate_host(cond_host, tokens_host, NEW_TOKENS, CFG_SCALE, -1, TEMP, TOP_K, TOP_P, True, 2000 + i)
+            if world > 1:
+                dist.all_gather_into_tensor(gathered, tokens_host.to(dev, non_blocking=True))
+        e2e_step(0)
+        fence()
+        t0 = time.perf_counter()
+        for i in range(args.steps):
+            e2e_step(i + 1)
+        fence()
+        e2e_s = torch.tensor([time.perf_counter() - t0], device=dev)
+        if world > 1:
+            dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+        e2e_s = float(e2e_s.item())
+        clocks = sampler.stop() if rank == 0 else None
+
+    tokens_per_step = B_LOCAL * NEW_TOKENS * world
+    value = tokens_per_step * args.steps / (ms * 1e-3)
+    if rank == 0:
+        pk, src = peaks()
+        cfg = model.config
+        geo_hidden = model.layers[0].feed_forward.w1.weight.shape[0]
+
+        class G:  # tiny adapter for algorithmic_bytes_generate
+            dim, n_layer, hidden_dim = cfg.dim, cfg.n_layer, geo_hidden
+        step_bytes = algorithmic_bytes_generate(G, 2 * B_LOCAL, 1, NEW_TOKENS, cfg.vocab_size)
+        roof = attention_kernel_roofline(dev, 2 * B_LOCAL, cfg.n_head, 584, NEW_TOKENS, pk["hbm_gbs"], src)
+        step_gbs = step_bytes / (ms / args.steps * 1e-3) / 1e9
+        roof["whole_step_achieved_gbs"] = round(step_gbs, 1)
+        roof["whole_step_frac"] = round(step_gbs / pk["hbm_gbs"], 4)
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            cpu, _ = cpu_reference_sample(args.ref_decode_steps)
+        line = {"metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 2), "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "config": workload_config(world), "clocks": clocks,
+                "e2e": {"value": round(tokens_per_step * args.steps / e2e_s, 1), "unit": UNIT,
+                        "h2d_bytes_per_step": B_LOCAL * 8 * world, "d2h_bytes_per_step": B_LOCAL * NEW_TOKENS * 4 * world},
+                "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="vlg", choices=["vlg", "reference"])
+    ap.add_argument("--ref-decode-steps", type=int, default=5, help="decode steps per CPU-reference sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_vlg(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -73,6 +73,9 @@ struct vlg_ctx {
   int rows = 0;
   bool has_mask = false;
   bool force_generic_attn = false;   // VLG_ATTN=generic: A/B the two attention kernels
+  // graph capture is illegal on the legacy default stream (torch's default): such callers are forked onto this one
+  cudaStream_t own_stream = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   // cached decode-step graph
   cudaGraphExec_t graph = nullptr;
   uint64_t step_kernels = 0;   // kernels per replayed decode step
@@ -237,6 +240,9 @@ extern "C" int vlg_ctx_create(const vlg_geometry* g, const vlg_weights* w, int m
   c->L = L;
   const char* env = getenv("VLG_ATTN");
   c->force_generic_attn = env && strcmp(env, "generic") == 0;
+  VLG_CUDA(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+  VLG_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+  VLG_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
   // the reference allocates zeroed caches (gpt.py:174-175); do it once so no stale NaN bit patterns exist
   VLG_CUDA(cudaMemset(c->ws + L.k_cache, 0, L.h - L.k_cache));
   VLG_CUDA(cudaMemset(c->state(), 0, sizeof(StepState)));
@@ -248,6 +254,9 @@ extern "C" int vlg_ctx_create(const vlg_geometry* g, const vlg_weights* w, int m
 extern "C" void vlg_ctx_destroy(vlg_ctx* c) {
   if (!c) return;
   if (c->graph) cudaGraphExecDestroy(c->graph);
+  if (c->own_stream) cudaStreamDestroy(c->own_stream);
+  if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+  if (c->ev_join) cudaEventDestroy(c->ev_join);
   delete c;
 }
 
@@ -324,9 +333,25 @@ extern "C" int vlg_mlp(vlg_ctx* c, int which, const void* x_dev, void* out_dev, 
   return launch_gemm(g.dtype, EPI_STORE, c->at<void>(c->L.mlp_tmp), fc2, n, outw, mid, P2, st);
 }
 
+static int generate_on(vlg_ctx* c, const vlg_generate_params* pp, const void* cond_dev, const void* uncond_dev,
+                       const uint8_t* emb_masks_dev, int32_t* tokens_dev, cudaStream_t stream);
+
 extern "C" int vlg_generate(vlg_ctx* c, const vlg_generate_params* pp, const void* cond_dev, const void* uncond_dev,
                             const uint8_t* emb_masks_dev, int32_t* tokens_dev, void* stream) {
   VLG_REQUIRE(c && pp && cond_dev && tokens_dev, "vlg_generate: null pointer");
+  cudaStream_t user = (cudaStream_t)stream;
+  const bool legacy = user == nullptr || user == cudaStreamLegacy || user == cudaStreamPerThread;
+  if (!legacy) return generate_on(c, pp, cond_dev, uncond_dev, emb_masks_dev, tokens_dev, user);
+  VLG_CUDA(cudaEventRecord(c->ev_fork, user));
+  VLG_CUDA(cudaStreamWaitEvent(c->own_stream, c->ev_fork, 0));
+  int rc = generate_on(c, pp, cond_dev, uncond_dev, emb_masks_dev, tokens_dev, c->own_stream);
+  VLG_CUDA(cudaEventRecord(c->ev_join, c->own_stream));
+  VLG_CUDA(cudaStreamWaitEvent(user, c->ev_join, 0));
+  return rc;
+}
+
+static int generate_on(vlg_ctx* c, const vlg_generate_params* pp, const void* cond_dev, const void* uncond_dev,
+                       const uint8_t* emb_masks_dev, int32_t* tokens_dev, cudaStream_t stream) {
   const vlg_generate_params p = *pp;
   const vlg_geometry& g = c->g;
   VLG_REQUIRE(g.model_type == VLG_C2I || g.model_type == VLG_T2I, "vlg_generate: model type %d has no token sampler", g.model_type);

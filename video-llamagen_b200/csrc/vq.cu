@@ -173,11 +173,11 @@ static int launch_vq(const float* z, const float* cb, int64_t* idx, float* zq, f
 extern "C" int vlg_vq_argmin(const float* z_dev, const float* codebook_dev, int64_t* idx_dev, float* zq_dev,
                              float* scratch_dev, int64_t B, int C, int64_t HW, int n_e, int l2_norm, void* stream) {
   using namespace vlg;
-  VLG_REQUIRE(z_dev && codebook_dev && idx_dev && scratch_dev, "vlg_vq_argmin: null pointer");
   VLG_REQUIRE(B >= 0 && HW >= 0 && n_e > 0, "vlg_vq_argmin: bad sizes B=%lld HW=%lld n_e=%d", (long long)B,
               (long long)HW, n_e);
   int64_t N = B * HW;
-  if (N == 0) return VLG_OK;
+  if (N == 0) return VLG_OK;   // empty batch: nothing to do (torch hands out null pointers for empty tensors)
+  VLG_REQUIRE(z_dev && codebook_dev && idx_dev && scratch_dev, "vlg_vq_argmin: null pointer");
   VLG_REQUIRE(N / ((int64_t)kVqThreads) < (1ll << 31), "vlg_vq_argmin: too many latents");
   cudaStream_t st = (cudaStream_t)stream;
   switch (C) {
@@ -194,9 +194,9 @@ extern "C" int vlg_vq_argmin(const float* z_dev, const float* codebook_dev, int6
 extern "C" int vlg_codebook_gather(const int64_t* idx_dev, const float* codebook_dev, float* out_dev, int64_t B, int C,
                                    int64_t HW, int n_e, int l2_norm, int channel_first, void* stream) {
   using namespace vlg;
-  VLG_REQUIRE(idx_dev && codebook_dev && out_dev, "vlg_codebook_gather: null pointer");
   int64_t N = B * HW;
   if (N == 0) return VLG_OK;
+  VLG_REQUIRE(idx_dev && codebook_dev && out_dev, "vlg_codebook_gather: null pointer");
   cudaStream_t st = (cudaStream_t)stream;
   unsigned blocks = (unsigned)((N + 255) / 256);
   switch (C) {
