@@ -207,6 +207,9 @@ int vlg_attn_decode(const void* q_dev, const void* k_cache_dev, const void* v_ca
                     int impl, void* scratch_dev, size_t scratch_bytes, void* stream);
 size_t vlg_attn_scratch_bytes(int rows, int H, int D, int S_max);
 
+/* instrumentation (VLG_GEMM_DEBUG & 4): globaltimer phase stamps of CTA 0 of the last tcgen05 GEMM; synchronises */
+int vlg_debug_gemm_timestamps(unsigned long long* out16_host);
+
 #ifdef __cplusplus
 }
 #endif

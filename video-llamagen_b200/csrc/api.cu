@@ -7,6 +7,7 @@
 // with no host synchronisation and no per-step host work besides cudaGraphLaunch.
 #include <stdlib.h>
 #include <vector>
+#include <cuda_profiler_api.h>
 
 #include "common.cuh"
 #include "kernels.h"
@@ -424,7 +425,16 @@ static int generate_on(vlg_ctx* c, const vlg_generate_params* pp, const void* co
       c->key = k;
       c->step_kernels = launches_after - launches_before;
     }
-    for (int i = 0; i < N - 1; ++i) VLG_CUDA(cudaGraphLaunch(c->graph, st));
+    // VLG_PROFILE_STEP=k: bracket decode steps k, k+1 of every generate() with cudaProfilerStart/Stop so that
+    // `ncu --profile-from-start off` captures a mid-sequence step without stepping through 100k launches.
+    static const int prof_step = [] { const char* e = getenv("VLG_PROFILE_STEP"); return e ? atoi(e) : -1; }();
+    static const bool no_graph = [] { const char* e = getenv("VLG_NO_GRAPH"); return e && e[0] == '1'; }();
+    for (int i = 0; i < N - 1; ++i) {
+      if (i == prof_step) { VLG_CUDA(cudaStreamSynchronize(st)); cudaProfilerStart(); }
+      if (no_graph) { if ((rc = decode_step(c, p, st))) return rc; count_launches(0 - c->step_kernels); }
+      else VLG_CUDA(cudaGraphLaunch(c->graph, st));
+      if (prof_step >= 0 && i == prof_step + 1) { VLG_CUDA(cudaStreamSynchronize(st)); cudaProfilerStop(); }
+    }
     count_launches((uint64_t)(N - 1) * c->step_kernels);
   }
   if (tokens_dev != c->at<int32_t>(c->L.seq))

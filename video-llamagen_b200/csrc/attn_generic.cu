@@ -38,6 +38,8 @@ attn_decode_generic_kernel(const T* __restrict__ q, const T* __restrict__ kc, co
 
   const int rh = blockIdx.x, split = blockIdx.y;
   const int row = rh / H;
+  pdl_launch_dependents();
+  pdl_wait();
   const int pos = pos_ptr ? *pos_ptr : pos_imm;
   const int n = pos + 1;
   int chunk = (n + n_splits - 1) / n_splits;
@@ -132,6 +134,8 @@ attn_decode_generic_kernel(const T* __restrict__ q, const T* __restrict__ kc, co
 template <typename T, int D>
 __global__ void attn_combine_kernel(const float* __restrict__ part, T* __restrict__ out, int n_splits) {
   const int rh = blockIdx.x, d = threadIdx.x;
+  pdl_launch_dependents();
+  pdl_wait();
   const float* pp = part + (size_t)rh * n_splits * (D + 2);
   float mm = -INFINITY;
   for (int s = 0; s < n_splits; ++s) mm = fmaxf(mm, pp[s * (D + 2)]);
@@ -168,12 +172,12 @@ static int launch_typed(const AttnArgs& a, cudaStream_t st) {
     VLG_REQUIRE(a.scratch && a.scratch_bytes >= (size_t)rh * n_splits * (a.D + 2) * sizeof(float),
                 "attn: scratch too small for %d splits", n_splits);
   }
-  attn_decode_generic_kernel<T, 64><<<dim3(rh, n_splits), kAttnThreads, 0, st>>>(
-      (const T*)a.q, (const T*)a.k_cache, (const T*)a.v_cache, (T*)a.out, a.scratch, a.H, a.S_max, a.pos_ptr,
-      a.pos_imm, a.prefix_mask, a.T_prefix, n_splits);
+  VLG_CUDA(launch_kernel(attn_decode_generic_kernel<T, 64>, dim3(rh, n_splits), dim3(kAttnThreads), 0, st, (const T*)a.q,
+                         (const T*)a.k_cache, (const T*)a.v_cache, (T*)a.out, a.scratch, a.H, a.S_max, a.pos_ptr,
+                         a.pos_imm, a.prefix_mask, a.T_prefix, n_splits));
   VLG_LAUNCH_CHECK();
   if (n_splits > 1) {
-    attn_combine_kernel<T, 64><<<rh, 64, 0, st>>>(a.scratch, (T*)a.out, n_splits);
+    VLG_CUDA(launch_kernel(attn_combine_kernel<T, 64>, dim3(rh), dim3(64), 0, st, (const float*)a.scratch, (T*)a.out, n_splits));
     VLG_LAUNCH_CHECK();
   }
   return VLG_OK;

@@ -52,6 +52,8 @@ attn_decode_tma_kernel(const __grid_constant__ TensorMap tmK, const __grid_const
     fence_mbar_init();
   }
   __syncthreads();
+  pdl_launch_dependents();
+  pdl_wait();                                // q, the newest K/V row and the position come from the previous kernels
 
   const int pos = pos_ptr ? *pos_ptr : pos_imm;
   const int n = pos + 1;
@@ -61,7 +63,7 @@ attn_decode_tma_kernel(const __grid_constant__ TensorMap tmK, const __grid_const
 
   if (warp == kCW) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    if (elect_one()) {
       uint32_t gt = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         const int rh = item / n_splits, split = item - rh * n_splits;
@@ -222,6 +224,8 @@ attn_decode_tma_kernel(const __grid_constant__ TensorMap tmK, const __grid_const
 // folds the split partials (same layout as the generic kernel's): out = sum_s o_s e^{m_s - M} / sum_s l_s e^{m_s - M}
 __global__ void attn_tma_combine_kernel(const float* __restrict__ part, __nv_bfloat16* __restrict__ out, int n_splits) {
   const int rh = blockIdx.x, d = threadIdx.x;
+  pdl_launch_dependents();
+  pdl_wait();
   const float* pp = part + (size_t)rh * n_splits * 66;
   float mm = -INFINITY;
   for (int s = 0; s < n_splits; ++s) mm = fmaxf(mm, pp[s * 66]);
@@ -267,12 +271,13 @@ int launch_attn_tma(int dtype, const AttnArgs& a, cudaStream_t st) {
   }
   const int n_items = n_rh * n_splits;
   const int grid = n_items < sms ? n_items : sms;
-  attn_decode_tma_kernel<<<grid, kAttnTmaThreads, smem, st>>>(
-      tmK, tmV, (const __nv_bfloat16*)a.q, (__nv_bfloat16*)a.out, a.scratch, n_rh, a.H, a.S_max, a.pos_ptr, a.pos_imm,
-      a.prefix_mask, a.T_prefix, n_splits);
+  VLG_CUDA(launch_kernel(attn_decode_tma_kernel, dim3(grid), dim3(kAttnTmaThreads), (size_t)smem, st, tmK, tmV,
+                         (const __nv_bfloat16*)a.q, (__nv_bfloat16*)a.out, a.scratch, n_rh, a.H, a.S_max, a.pos_ptr,
+                         a.pos_imm, a.prefix_mask, a.T_prefix, n_splits));
   VLG_LAUNCH_CHECK();
   if (n_splits > 1) {
-    attn_tma_combine_kernel<<<n_rh, 64, 0, st>>>(a.scratch, (__nv_bfloat16*)a.out, n_splits);
+    VLG_CUDA(launch_kernel(attn_tma_combine_kernel, dim3(n_rh), dim3(64), 0, st, (const float*)a.scratch,
+                           (__nv_bfloat16*)a.out, n_splits));
     VLG_LAUNCH_CHECK();
   }
   return VLG_OK;

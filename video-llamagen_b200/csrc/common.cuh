@@ -36,6 +36,35 @@ void count_launches(uint64_t n);
     VLG_CUDA(cudaGetLastError()); \
   } while (0)
 
+// ------------------------------------------------------------------ programmatic dependent launch (PDL)
+// Every decode-step kernel is launched with programmatic stream serialization: it may start while its
+// predecessor drains, runs its input-independent prologue (barrier init, TMEM alloc, descriptor prefetch, weight
+// prefetch), and only then waits for the predecessor's memory with griddepcontrol.wait.  VLG_PDL=0 disables it.
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                 Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
+#ifdef __CUDACC__
+// wait until the preceding kernel's writes are visible (no-op when launched without the PDL attribute)
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// allow the next kernel in the stream to begin launching
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
+
 // ------------------------------------------------------------------ small device utils
 constexpr int kWarp = 32;
 

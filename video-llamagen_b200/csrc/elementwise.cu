@@ -16,6 +16,8 @@ rmsnorm_kernel(const T* __restrict__ x, const T* __restrict__ w, T* __restrict__
   __shared__ float s_part[kNormThreads / 32];
   const int r = blockIdx.x, nvec = dim / 8;
   const T* xr = x + (size_t)r * dim;
+  pdl_launch_dependents();
+  pdl_wait();
   float v[kNormMaxVec][8];
   float ss = 0.f;
 #pragma unroll
@@ -51,10 +53,11 @@ int launch_rmsnorm(int dtype, const void* x, const void* w, void* out, int rows,
   VLG_REQUIRE(dim % 8 == 0 && dim <= 8 * kNormThreads * kNormMaxVec, "rmsnorm: dim %d unsupported", dim);
   if (rows == 0) return VLG_OK;
   if (dtype == VLG_BF16)
-    rmsnorm_kernel<__nv_bfloat16><<<rows, kNormThreads, 0, st>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)w,
-                                                                 (__nv_bfloat16*)out, dim, eps);
+    VLG_CUDA(launch_kernel(rmsnorm_kernel<__nv_bfloat16>, dim3(rows), dim3(kNormThreads), 0, st, (const __nv_bfloat16*)x,
+                           (const __nv_bfloat16*)w, (__nv_bfloat16*)out, dim, eps));
   else
-    rmsnorm_kernel<float><<<rows, kNormThreads, 0, st>>>((const float*)x, (const float*)w, (float*)out, dim, eps);
+    VLG_CUDA(launch_kernel(rmsnorm_kernel<float>, dim3(rows), dim3(kNormThreads), 0, st, (const float*)x, (const float*)w,
+                           (float*)out, dim, eps));
   VLG_LAUNCH_CHECK();
   return VLG_OK;
 }
@@ -70,6 +73,8 @@ __global__ void gather_rows_kernel(const T* __restrict__ table, T* __restrict__ 
                                    const int* __restrict__ col_ptr, int col_off, const int64_t* __restrict__ labels,
                                    int B, int null_class, int table_rows) {
   const int r = blockIdx.x;
+  pdl_launch_dependents();
+  pdl_wait();
   int64_t id;
   if (idx64) id = idx64[r];
   else if (seq) id = seq[(size_t)(r % B) * seq_stride + (*col_ptr + col_off)];
@@ -86,12 +91,12 @@ int launch_gather(int dtype, const void* table, void* out, int rows, int dim, co
                   int null_class, int table_rows, cudaStream_t st) {
   if (rows == 0) return VLG_OK;
   if (dtype == VLG_BF16)
-    gather_rows_kernel<__nv_bfloat16><<<rows, 128, 0, st>>>((const __nv_bfloat16*)table, (__nv_bfloat16*)out, rows,
-                                                            dim, idx64, seq, seq_stride, col_ptr, col_off, labels, B,
-                                                            null_class, table_rows);
+    VLG_CUDA(launch_kernel(gather_rows_kernel<__nv_bfloat16>, dim3(rows), dim3(128), 0, st, (const __nv_bfloat16*)table,
+                           (__nv_bfloat16*)out, rows, dim, idx64, seq, seq_stride, col_ptr, col_off, labels, B,
+                           null_class, table_rows));
   else
-    gather_rows_kernel<float><<<rows, 128, 0, st>>>((const float*)table, (float*)out, rows, dim, idx64, seq,
-                                                    seq_stride, col_ptr, col_off, labels, B, null_class, table_rows);
+    VLG_CUDA(launch_kernel(gather_rows_kernel<float>, dim3(rows), dim3(128), 0, st, (const float*)table, (float*)out,
+                           rows, dim, idx64, seq, seq_stride, col_ptr, col_off, labels, B, null_class, table_rows));
   VLG_LAUNCH_CHECK();
   return VLG_OK;
 }

@@ -9,6 +9,8 @@
 //    weight stream over the SMs; activations are re-read from L2 (evict-last), weights evict-first.
 //  * fp32: CUDA-core FMA only (no TF32), fixed summation order -- the exact path behind the greedy
 //    bit-exact contract.  One warp owns 8 output columns, lanes split K, 8 rows per pass.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "epilogue.cuh"
 
@@ -28,10 +30,19 @@ template <int BN> struct GemmCfg {
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
+// phase timestamps of CTA 0 (globaltimer ns), written when dbg & 4: microbenchmark instrumentation only
+__device__ unsigned long long g_gemm_ts[16];
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+#define GEMM_TS(i) do { if ((dbg & 4) && blockIdx.x == 0 && blockIdx.y == 0) g_gemm_ts[i] = gtime(); } while (0)
+
 template <int BN, int EPI>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_tc_kernel(const __grid_constant__ TensorMap tmA, const __grid_constant__ TensorMap tmB, int rows, int K,
-                    EpiParams P) {
+                    EpiParams P, int dbg) {
   using Cfg = GemmCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -43,6 +54,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ TensorMap tmA, const __grid_constant
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n0 = blockIdx.x * BN, m0 = blockIdx.y * kBM;
   const int nkb = K / kBK;
+  if (threadIdx.x == 0) GEMM_TS(0);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -56,24 +68,41 @@ gemm_bf16_tc_kernel(const __grid_constant__ TensorMap tmA, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_acc = *tmem_slot;
+  if (threadIdx.x == 0) GEMM_TS(1);
 
+  pdl_launch_dependents();
   if (warp == 0) {
-    if (lane == 0) {
-      for (int kb = 0; kb < nkb; ++kb) {
+    if (elect_one()) {   // elect.sync: the compiler then knows one thread is active and feeds the uniform datapath directly
+      // The weight tiles do not depend on the previous kernel: start streaming them for the first ring pass before
+      // waiting for its output, so the weight stream overlaps the predecessor's tail.
+      const int pre = nkb < Cfg::kStages ? nkb : Cfg::kStages;
+      // dbg (microbenchmarks only): bit 0 skips the activation loads, bit 1 the weight loads
+      const uint32_t tx = ((dbg & 1) ? 0 : kBM * kBK * 2) + ((dbg & 2) ? 0 : BN * kBK * 2);
+      for (int kb = 0; kb < pre; ++kb) {
+        if (tx) mbar_expect_tx(&full[kb], tx); else mbar_arrive(&full[kb]);
+        if (!(dbg & 2)) tma_load_2d_hint(smem + kb * Cfg::kStageBytes + Cfg::kABytes, &tmB, &full[kb], kb * kBK, n0, kEvictFirst);
+      }
+      GEMM_TS(2);
+      pdl_wait();
+      GEMM_TS(3);
+      for (int kb = 0; kb < pre; ++kb)
+        if (!(dbg & 1)) tma_load_2d_hint(smem + kb * Cfg::kStageBytes, &tmA, &full[kb], kb * kBK, m0, kEvictLast);
+      for (int kb = pre; kb < nkb; ++kb) {
         const int s = kb % Cfg::kStages, it = kb / Cfg::kStages;
         mbar_wait(&empty[s], (it & 1) ^ 1);
         uint8_t* a = smem + s * Cfg::kStageBytes;
-        mbar_expect_tx(&full[s], kBM * kBK * 2 + BN * kBK * 2);
-        tma_load_2d_hint(a, &tmA, &full[s], kb * kBK, m0, kEvictLast);
-        tma_load_2d_hint(a + Cfg::kABytes, &tmB, &full[s], kb * kBK, n0, kEvictFirst);
+        if (tx) mbar_expect_tx(&full[s], tx); else mbar_arrive(&full[s]);
+        if (!(dbg & 1)) tma_load_2d_hint(a, &tmA, &full[s], kb * kBK, m0, kEvictLast);
+        if (!(dbg & 2)) tma_load_2d_hint(a + Cfg::kABytes, &tmB, &full[s], kb * kBK, n0, kEvictFirst);
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one()) {
       constexpr uint32_t idesc = umma_idesc_bf16(kBM, BN);
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % Cfg::kStages, it = kb / Cfg::kStages;
         mbar_wait(&full[s], it & 1);
+        if (kb == 0) GEMM_TS(4);
         tc_fence_after();
         const uint32_t a_addr = smem_u32(smem + s * Cfg::kStageBytes);
         const uint64_t adesc = umma_desc_sw128(a_addr), bdesc = umma_desc_sw128(a_addr + Cfg::kABytes);
@@ -83,11 +112,14 @@ gemm_bf16_tc_kernel(const __grid_constant__ TensorMap tmA, const __grid_constant
         umma_commit(&empty[s]);             // frees the smem stage once these MMAs retire
       }
       umma_commit(acc_ready);
+      GEMM_TS(5);
     }
   } else {
     const int quad = warp & 3;              // TMEM lanes [32*quad, 32*quad+32) are the ones this warp may read
     const int r = m0 + quad * 32 + lane;
+    pdl_wait();                             // the epilogue reads predecessor outputs (residual, position)
     mbar_wait(acc_ready, 0);
+    if (threadIdx.x == 64) GEMM_TS(6);
     tc_fence_after();
 #pragma unroll
     for (int c = 0; c < BN; c += 16) {
@@ -99,9 +131,11 @@ gemm_bf16_tc_kernel(const __grid_constant__ TensorMap tmA, const __grid_constant
       }
     }
   }
+  if (threadIdx.x == 64) GEMM_TS(7);
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc<Cfg::kTmemCols>(tmem_acc);
+  if (threadIdx.x == 32) GEMM_TS(8);
 }
 
 template <int BN, int EPI>
@@ -119,7 +153,8 @@ static int launch_tc(const void* x, const void* w, int rows, int N, int K, const
     attr_set = true;
   }
   dim3 grid(N / BN, (rows + kBM - 1) / kBM);
-  kern<<<grid, kGemmThreads, Cfg::kSmemBytes, st>>>(tmA, tmB, rows, K, P);
+  static const int dbg = [] { const char* e = getenv("VLG_GEMM_DEBUG"); return e ? atoi(e) : 0; }();
+  VLG_CUDA(launch_kernel(kern, grid, dim3(kGemmThreads), Cfg::kSmemBytes, st, tmA, tmB, rows, K, P, dbg));
   VLG_LAUNCH_CHECK();
   return VLG_OK;
 }
@@ -132,6 +167,8 @@ __global__ void __launch_bounds__(kF32Warps * 32)
 gemm_f32_kernel(const float* __restrict__ x, const float* __restrict__ w, int rows, int N, int K, EpiParams P) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n0 = (blockIdx.x * kF32Warps + warp) * 8;
+  pdl_launch_dependents();
+  pdl_wait();
   if (n0 >= N) return;
   for (int r0 = 0; r0 < rows; r0 += 8) {
     float acc[8][8];
@@ -173,8 +210,8 @@ gemm_f32_kernel(const float* __restrict__ x, const float* __restrict__ w, int ro
 template <int EPI>
 static int launch_f32(const void* x, const void* w, int rows, int N, int K, const EpiParams& P, cudaStream_t st) {
   int groups = N / 8;
-  gemm_f32_kernel<EPI><<<(groups + kF32Warps - 1) / kF32Warps, kF32Warps * 32, 0, st>>>(
-      static_cast<const float*>(x), static_cast<const float*>(w), rows, N, K, P);
+  VLG_CUDA(launch_kernel(gemm_f32_kernel<EPI>, dim3((groups + kF32Warps - 1) / kF32Warps), dim3(kF32Warps * 32), 0, st,
+                         static_cast<const float*>(x), static_cast<const float*>(w), rows, N, K, P));
   VLG_LAUNCH_CHECK();
   return VLG_OK;
 }
@@ -184,6 +221,13 @@ static int launch_f32(const void* x, const void* w, int rows, int N, int K, cons
 // beyond that (every CTA re-reads the whole activation matrix from L2).
 template <int EPI>
 static int launch_tc_auto(const void* x, const void* w, int rows, int N, int K, const EpiParams& P, cudaStream_t st) {
+  if constexpr (EPI == EPI_STORE) {   // tile-width override for microbenchmarks (plain-store epilogue only)
+    static const int bn = [] { const char* e = getenv("VLG_GEMM_BN"); return e ? atoi(e) : 0; }();
+    if (bn == 16) return launch_tc<16, EPI>(x, w, rows, N, K, P, st);
+    if (bn == 32) return launch_tc<32, EPI>(x, w, rows, N, K, P, st);
+    if (bn == 64 && N % 64 == 0) return launch_tc<64, EPI>(x, w, rows, N, K, P, st);
+    if (bn == 128 && N % 128 == 0) return launch_tc<128, EPI>(x, w, rows, N, K, P, st);
+  }
   if (N % 32 == 0 && N / 32 >= 96) return launch_tc<32, EPI>(x, w, rows, N, K, P, st);
   return launch_tc<16, EPI>(x, w, rows, N, K, P, st);
 }
@@ -225,4 +269,10 @@ extern "C" int vlg_linear(const void* x_dev, const void* w_dev, void* out_dev, i
   P.out = out_dev;
   P.ld_out = N;
   return launch_gemm(dtype, out_f32 ? EPI_STORE_F32 : EPI_STORE, x_dev, w_dev, rows, N, K, P, (cudaStream_t)stream);
+}
+
+// microbenchmark instrumentation: phase timestamps (ns) of CTA 0 of the last tcgen05 GEMM run with VLG_GEMM_DEBUG & 4
+extern "C" int vlg_debug_gemm_timestamps(unsigned long long* out16_host) {
+  VLG_CUDA(cudaMemcpyFromSymbol(out16_host, vlg::g_gemm_ts, sizeof(unsigned long long) * 16));
+  return VLG_OK;
 }

@@ -77,6 +77,8 @@ __global__ void __launch_bounds__(kSampThreads, 1) cfg_sample_kernel(SampleArgs 
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int V = a.V;
   BlockRed red{s_redf, s_redi};
+  pdl_launch_dependents();
+  pdl_wait();
 
   const int step = a.step_ptr ? *a.step_ptr : 0;
   const bool two_halves = a.rows == 2 * a.B;
@@ -295,7 +297,7 @@ int launch_sample(const SampleArgs& a, cudaStream_t st) {
     VLG_CUDA(cudaFuncSetAttribute(cfg_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = smem;
   }
-  cfg_sample_kernel<<<a.B, kSampThreads, smem, st>>>(a);
+  VLG_CUDA(launch_kernel(cfg_sample_kernel, dim3(a.B), dim3(kSampThreads), smem, st, a));
   VLG_LAUNCH_CHECK();
   return VLG_OK;
 }

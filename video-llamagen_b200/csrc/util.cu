@@ -1,5 +1,6 @@
 // Error plumbing, launch accounting and host-side TMA descriptor encoding.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <atomic>
 #include <cuda.h>
 #include <cudaTypedefs.h>
@@ -24,6 +25,15 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
 }
 
 void count_launches(uint64_t n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("VLG_PDL");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v != 0;
+}
 
 int num_sms() {
   static int n = 0;
