@@ -5,7 +5,7 @@
 // one FMA, so the design goal is bytes in flight, not flops:
 //   * persistent CTAs (one per SM), work items = (row, head[, sequence split]) dealt round-robin;
 //   * warp 0 is a TMA producer: it streams 32-position K and V tiles (4 KB each, 128-byte swizzle) through a
-//     24-stage shared-memory ring (192 KB in flight per SM) and runs ahead ACROSS work items, so the pipe
+//     16-stage shared-memory ring (128 KB in flight per SM) and runs ahead ACROSS work items, so the pipe
 //     never drains between the short (<= 19-tile) sequences of one step;
 //   * 8 consumer warps each own every 8th tile: one lane per cache position for q.k (the swizzle makes the
 //     16-byte row reads conflict-free), warp-level online softmax in the exp2 domain, then 8 lanes per
@@ -19,22 +19,24 @@ namespace vlg {
 
 constexpr int kTile = 32;                   // cache positions per TMA tile
 constexpr int kCW = 8;                      // consumer warps
-constexpr int kStagesA = 24;                // ring depth (multiple of kCW: stage s always belongs to warp s % kCW)
+constexpr int kStagesA = 16;                // ring depth (multiple of kCW: stage s always belongs to warp s % kCW)
 constexpr int kTileBytes = kTile * 128;     // one K or V tile (D = 64 bf16 = 128 B per position)
 constexpr int kStageBytesA = 2 * kTileBytes;
 constexpr int kAttnTmaThreads = (kCW + 1) * 32;
 constexpr int kMaxSplitsT = 32;
 
+constexpr int kSlots = 16;                  // in-flight work items per CTA whose partial states await their merge
+
 struct ItemSlot { float m, l, pad0, pad1; float o[64]; };
 
 struct AttnTmaSmem {
   uint8_t ring[kStagesA][kStageBytesA];     // 1024-byte aligned (swizzle atom = 8 rows x 128 B)
-  ItemSlot slot[2][kCW];
+  ItemSlot slot[kSlots][kCW];
   float p[kCW][kTile];
   uint64_t full[kStagesA], empty[kStagesA];
+  unsigned cnt[kSlots];                     // warps that have published their partial for the item in this slot
+  volatile unsigned gen[kSlots];            // how many items have been merged out of this slot (slot reuse gate)
 };
-
-__device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, %0;" ::"n"(kCW * 32) : "memory"); }
 
 __global__ void __launch_bounds__(kAttnTmaThreads, 1)
 attn_decode_tma_kernel(const __grid_constant__ TensorMap tmK, const __grid_constant__ TensorMap tmV,
@@ -49,6 +51,7 @@ attn_decode_tma_kernel(const __grid_constant__ TensorMap tmK, const __grid_const
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
     for (int s = 0; s < kStagesA; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], 1); }
+    for (int s = 0; s < kSlots; ++s) { sm.cnt[s] = 0; sm.gen[s] = 0; }
     fence_mbar_init();
   }
   __syncthreads();
@@ -87,32 +90,28 @@ attn_decode_tma_kernel(const __grid_constant__ TensorMap tmK, const __grid_const
   const float kScale = 0.125f * 1.4426950408889634f;   // 1/sqrt(64) * log2(e)
   uint32_t gt0 = 0;                                     // tiles issued before the current item
   int item_i = 0;
-  uint4 qraw[8];
-  if (blockIdx.x < n_items) {
-    const uint4* qp = reinterpret_cast<const uint4*>(q + (size_t)(blockIdx.x / n_splits) * 64);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) qraw[i] = qp[i];
-  }
   for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++item_i) {
     const int rh = item / n_splits, split = item - rh * n_splits;
     const int s_begin = split * chunk, s_end = min(n, s_begin + chunk);
     const int n_tiles = s_end > s_begin ? (s_end - s_begin + kTile - 1) / kTile : 0;
+    const int w0 = (int)(gt0 % kCW);                                  // warp that owns the item's first tile
+    const int participants = n_tiles < kCW ? n_tiles : kCW;           // warps (w0 + k) % kCW, k < participants
+    const int first_t = (warp - w0 + kCW) % kCW;                      // first tile of this item owned by this warp
+    const uint32_t gt_item = gt0;
+    gt0 += n_tiles;
+    if (!(n_tiles > 0 ? first_t < n_tiles : warp == 0)) continue;     // no share in this item: move on, no sync
     const uint8_t* mrow = mask ? mask + (size_t)(rh / H) * T_prefix : nullptr;
 
     float qf[64];
+    {
+      const uint4* qp = reinterpret_cast<const uint4*>(q + (size_t)rh * 64);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      qf[8 * i + 0] = bf16lo(qraw[i].x) * kScale; qf[8 * i + 1] = bf16hi(qraw[i].x) * kScale;
-      qf[8 * i + 2] = bf16lo(qraw[i].y) * kScale; qf[8 * i + 3] = bf16hi(qraw[i].y) * kScale;
-      qf[8 * i + 4] = bf16lo(qraw[i].z) * kScale; qf[8 * i + 5] = bf16hi(qraw[i].z) * kScale;
-      qf[8 * i + 6] = bf16lo(qraw[i].w) * kScale; qf[8 * i + 7] = bf16hi(qraw[i].w) * kScale;
-    }
-    {  // prefetch the next item's query while this item's tiles are processed
-      const int nxt = item + gridDim.x;
-      if (nxt < n_items) {
-        const uint4* qp = reinterpret_cast<const uint4*>(q + (size_t)(nxt / n_splits) * 64);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) qraw[i] = qp[i];
+      for (int i = 0; i < 8; ++i) {
+        const uint4 qr = qp[i];
+        qf[8 * i + 0] = bf16lo(qr.x) * kScale; qf[8 * i + 1] = bf16hi(qr.x) * kScale;
+        qf[8 * i + 2] = bf16lo(qr.y) * kScale; qf[8 * i + 3] = bf16hi(qr.y) * kScale;
+        qf[8 * i + 4] = bf16lo(qr.z) * kScale; qf[8 * i + 5] = bf16hi(qr.z) * kScale;
+        qf[8 * i + 6] = bf16lo(qr.w) * kScale; qf[8 * i + 7] = bf16hi(qr.w) * kScale;
       }
     }
 
@@ -120,10 +119,8 @@ attn_decode_tma_kernel(const __grid_constant__ TensorMap tmK, const __grid_const
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc[i] = 0.f;
 
-    // first tile of this item owned by this warp: (gt0 + t) % kCW == warp
-    int t = (warp - (int)(gt0 % kCW) + kCW) % kCW;
-    for (; t < n_tiles; t += kCW) {
-      const uint32_t gt = gt0 + t, st = gt % kStagesA, it = gt / kStagesA;
+    for (int t = first_t; t < n_tiles; t += kCW) {
+      const uint32_t gt = gt_item + t, st = gt % kStagesA, it = gt / kStagesA;
       mbar_wait(&sm.full[st], it & 1);
       const uint8_t* kt = sm.ring[st];
       const uint8_t* vt = kt + kTileBytes;
@@ -166,57 +163,89 @@ attn_decode_tma_kernel(const __grid_constant__ TensorMap tmK, const __grid_const
       const float4 pb = *reinterpret_cast<const float4*>(&sm.p[warp][8 * g + 4]);
       const float pj[8] = {pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, pb.w};
 #pragma unroll
+      // Rows past the end of the prefix carry p = 0; their bytes are finite (the cache is zero-initialised once and only
+      // ever holds finite values; TMA zero-fills out-of-bounds rows), so no branch is needed to keep them out.
       for (int j = 0; j < 8; ++j) {
         const int row = 8 * g + j;
-        if (pj[j] != 0.f) {                             // skips masked / beyond-the-end rows (their bytes may be stale)
-          const uint4 vv = *reinterpret_cast<const uint4*>(vt + row * 128 + ((c ^ (row & 7)) << 4));
-          acc[0] = fmaf(pj[j], bf16lo(vv.x), acc[0]); acc[1] = fmaf(pj[j], bf16hi(vv.x), acc[1]);
-          acc[2] = fmaf(pj[j], bf16lo(vv.y), acc[2]); acc[3] = fmaf(pj[j], bf16hi(vv.y), acc[3]);
-          acc[4] = fmaf(pj[j], bf16lo(vv.z), acc[4]); acc[5] = fmaf(pj[j], bf16hi(vv.z), acc[5]);
-          acc[6] = fmaf(pj[j], bf16lo(vv.w), acc[6]); acc[7] = fmaf(pj[j], bf16hi(vv.w), acc[7]);
-        }
+        const uint4 vv = *reinterpret_cast<const uint4*>(vt + row * 128 + ((c ^ (row & 7)) << 4));
+        acc[0] = fmaf(pj[j], bf16lo(vv.x), acc[0]); acc[1] = fmaf(pj[j], bf16hi(vv.x), acc[1]);
+        acc[2] = fmaf(pj[j], bf16lo(vv.y), acc[2]); acc[3] = fmaf(pj[j], bf16hi(vv.y), acc[3]);
+        acc[4] = fmaf(pj[j], bf16lo(vv.z), acc[4]); acc[5] = fmaf(pj[j], bf16hi(vv.z), acc[5]);
+        acc[6] = fmaf(pj[j], bf16lo(vv.w), acc[6]); acc[7] = fmaf(pj[j], bf16hi(vv.w), acc[7]);
       }
       __syncwarp();                                     // all lanes finished reading the stage
       if (lane == 0) mbar_arrive(&sm.empty[st]);
     }
-    gt0 += n_tiles;
 
-    // ---- fold the 4 row groups of the warp, publish the warp's partial state
+    // ---- this warp's share of the item is done.  Warps flow through the items independently (no CTA barrier):
+    // every participant publishes its partial (m, l, o); the last one to arrive merges and writes the output.
     l = warp_sum(l);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 8);
       acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 16);
     }
-    ItemSlot& mine = sm.slot[item_i & 1][warp];
-    if (lane == 0) { mine.m = m; mine.l = l; }
-    if (lane < 8) {
-      *reinterpret_cast<float4*>(&mine.o[8 * c]) = make_float4(acc[0], acc[1], acc[2], acc[3]);
-      *reinterpret_cast<float4*>(&mine.o[8 * c + 4]) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+    const int sj = item_i % kSlots;
+    const unsigned my_gen = (unsigned)(item_i / kSlots);
+    if (lane == 0) {                                                  // slot reuse gate: previous occupant merged?
+      uint32_t spins = 0;
+      while (sm.gen[sj] != my_gen)
+        if (++spins > (1u << 26)) { printf("vlg: attention slot timeout\n"); __trap(); }
     }
-    consumer_bar();
-    if (warp == item_i % kCW) {                         // merge duty rotates over the consumer warps
-      const ItemSlot* sl = sm.slot[item_i & 1];
-      float mm = -INFINITY;
+    __syncwarp();
+    float o0 = 0.f, o1 = 0.f, lt = l, mm = m;
+    bool last = true;
+    if (participants <= 1) {
+      // single-warp item: lane L needs dims 2L, 2L+1 = acc[(2L) % 8 (+1)] of a lane with c == L / 4
+      const int src = lane >> 2, sel = (lane & 3) * 2;
 #pragma unroll
-      for (int w = 0; w < kCW; ++w) mm = fmaxf(mm, sl[w].m);
-      float lt = 0.f, o0 = 0.f, o1 = 0.f;
-#pragma unroll
-      for (int w = 0; w < kCW; ++w) {
-        const float a = sl[w].m == -INFINITY ? 0.f : exp2f(sl[w].m - mm);
-        lt = fmaf(sl[w].l, a, lt);
-        const float2 ov = *reinterpret_cast<const float2*>(&sl[w].o[2 * lane]);
-        o0 = fmaf(ov.x, a, o0);
-        o1 = fmaf(ov.y, a, o1);
+      for (int i = 0; i < 8; i += 2) {
+        const float a0 = __shfl_sync(0xffffffffu, acc[i], src), a1 = __shfl_sync(0xffffffffu, acc[i + 1], src);
+        if (sel == i) { o0 = a0; o1 = a1; }
       }
-      if (n_splits == 1) {
-        const float inv = 1.0f / lt;
-        *reinterpret_cast<uint32_t*>(out + (size_t)rh * 64 + 2 * lane) = pack_bf16(o0 * inv, o1 * inv);
-      } else {
-        float* pp = part + ((size_t)rh * n_splits + split) * 66;
-        *reinterpret_cast<float2*>(pp + 2 + 2 * lane) = make_float2(o0, o1);
-        if (lane == 0) { pp[0] = mm * 0.6931471805599453f; pp[1] = lt; }   // natural-log units for the combiner
+    } else {
+      ItemSlot& pub = sm.slot[sj][warp];
+      if (lane == 0) { pub.m = m; pub.l = l; }
+      if (lane < 8) {
+        *reinterpret_cast<float4*>(&pub.o[8 * c]) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        *reinterpret_cast<float4*>(&pub.o[8 * c + 4]) = make_float4(acc[4], acc[5], acc[6], acc[7]);
       }
+      __threadfence_block();
+      __syncwarp();
+      unsigned arrived = 0;
+      if (lane == 0) arrived = atomicAdd(&sm.cnt[sj], 1u);
+      arrived = __shfl_sync(0xffffffffu, arrived, 0);
+      last = arrived == (unsigned)participants - 1;
+      if (last) {
+        __threadfence_block();
+        const ItemSlot* sl = sm.slot[sj];
+        mm = -INFINITY;
+        for (int k = 0; k < participants; ++k) mm = fmaxf(mm, sl[(w0 + k) % kCW].m);
+        lt = 0.f;
+        for (int k = 0; k < participants; ++k) {
+          const ItemSlot& ps = sl[(w0 + k) % kCW];
+          const float a = ps.m == -INFINITY ? 0.f : exp2f(ps.m - mm);
+          lt = fmaf(ps.l, a, lt);
+          const float2 ov = *reinterpret_cast<const float2*>(&ps.o[2 * lane]);
+          o0 = fmaf(ov.x, a, o0);
+          o1 = fmaf(ov.y, a, o1);
+        }
+      }
+    }
+    if (!last) continue;
+    if (n_splits == 1) {
+      const float inv = 1.0f / lt;
+      *reinterpret_cast<uint32_t*>(out + (size_t)rh * 64 + 2 * lane) = pack_bf16(o0 * inv, o1 * inv);
+    } else {
+      float* pp = part + ((size_t)rh * n_splits + split) * 66;
+      *reinterpret_cast<float2*>(pp + 2 + 2 * lane) = make_float2(o0, o1);
+      if (lane == 0) { pp[0] = mm * 0.6931471805599453f; pp[1] = lt; }   // natural-log units for the combiner
+    }
+    __syncwarp();                                                     // all lanes are done with the slot
+    if (lane == 0) {
+      sm.cnt[sj] = 0;
+      __threadfence_block();
+      sm.gen[sj] = my_gen + 1;                                        // hand the slot to item_i + kSlots
     }
   }
 }
