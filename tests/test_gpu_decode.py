@@ -146,7 +146,13 @@ def test_gptl_cfg2_full_size_bf16():
     sub = cond[:8]
     toks = a[:8, :40].long()
     w16 = {k: v.to(DEV, torch.bfloat16) for k, v in w.items()}
-    ref = O.teacher_forced_logits(geo, w16, sub, toks)
+    ref = O.teacher_forced_logits(geo, w16, sub, toks)                 # reference algorithm, bf16, same GPU
+    truth = O.teacher_forced_logits(geo, {k: v.float() for k, v in w16.items()}, sub, toks)  # same weights, fp32 math
     rows = torch.cat([sub, torch.ones_like(sub) * 1000])
     ours = teacher_forced(m, rows, toks, 1).float()
-    assert torch.allclose(ours, ref, rtol=BF16_RTOL, atol=BF16_ATOL), (ours - ref).abs().max()
+    # The bf16 noise floor scales with the signal: SURVEY 8c calibrated atol 0.06 at logit rms 0.55.
+    scale = max(1.0, truth.pow(2).mean().sqrt().item() / 0.55)
+    assert torch.allclose(ours, ref, rtol=BF16_RTOL, atol=BF16_ATOL * scale), ((ours - ref).abs().max(), scale)
+    rms_ours = (ours - truth).pow(2).mean().sqrt().item()
+    rms_ref = (ref - truth).pow(2).mean().sqrt().item()
+    assert rms_ours <= 1.5 * rms_ref + 1e-4, (rms_ours, rms_ref)       # no noisier than the reference's own bf16 run

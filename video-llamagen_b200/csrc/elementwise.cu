@@ -17,6 +17,13 @@ rmsnorm_kernel(const T* __restrict__ x, const T* __restrict__ w, T* __restrict__
   const int r = blockIdx.x, nvec = dim / 8;
   const T* xr = x + (size_t)r * dim;
   pdl_launch_dependents();
+  // x depends on the previous kernel; the norm weight does not: fetch it before waiting
+  float g[kNormMaxVec][8];
+#pragma unroll
+  for (int i = 0; i < kNormMaxVec; ++i) {
+    int vi = threadIdx.x + i * kNormThreads;
+    if (vi < nvec) load8<T>(w + vi * 8, g[i]);
+  }
   pdl_wait();
   float v[kNormMaxVec][8];
   float ss = 0.f;
@@ -40,10 +47,9 @@ rmsnorm_kernel(const T* __restrict__ x, const T* __restrict__ w, T* __restrict__
   for (int i = 0; i < kNormMaxVec; ++i) {
     int vi = threadIdx.x + i * kNormThreads;
     if (vi < nvec) {
-      float g[8], o[8];
-      load8<T>(w + vi * 8, g);
+      float o[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = __fmul_rn(rnd<T>(__fmul_rn(v[i][j], rs)), g[j]);
+      for (int j = 0; j < 8; ++j) o[j] = __fmul_rn(rnd<T>(__fmul_rn(v[i][j], rs)), g[i][j]);
       store8<T>(out + (size_t)r * dim + vi * 8, o);
     }
   }

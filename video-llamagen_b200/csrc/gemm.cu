@@ -17,17 +17,24 @@
 namespace vlg {
 
 // ============================================================================ tcgen05 bf16 GEMM
-constexpr int kGemmThreads = 192;  // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
-constexpr int kBM = 128;
+constexpr int kMmaWarps = 2;       // MMA issuers: k-blocks alternate between them, one TMEM accumulator each
+constexpr int kGemmThreads = 32 * (1 + kMmaWarps + 4);  // warp 0: TMA producer, warps 1..kMmaWarps: MMA issuers (warp 1 owns TMEM), 4 epilogue warps
 constexpr int kBK = 64;            // 64 bf16 = one 128-byte swizzle row
 
-template <int BN> struct GemmCfg {
-  static constexpr int kABytes = kBM * kBK * 2;
+// BM = 128: output rows ride all 128 TMEM lanes.  BM = 64: "half subpartition" accumulator layout -- row m lives in
+// lane (m % 16) + 32 * (m / 16) (cute::UMMA::tmem_frg, M_MMA == 64) -- used where the activation tile, not the weight
+// stream, bounds the CTA (each CTA ingests the whole [BM x K] activation slab through its 64 B/clk L2 port).
+template <int BM, int BN> struct GemmCfg {
+  static constexpr int kABytes = BM * kBK * 2;
   static constexpr int kBBytes = (BN * kBK * 2 + 1023) / 1024 * 1024;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (BN <= 64) ? 8 : 6;
-  static constexpr int kTmemCols = BN < 32 ? 32 : BN;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  // The k-loop is latency-bound (one TMA round trip is ~1.3 us against ~0.05 us of MMA per k-block): the ring is as deep
+  // as shared memory allows so that (nearly) all of K is in flight at once.
+  static constexpr int kStagesRaw = (200 * 1024 / kStageBytes) < 24 ? (200 * 1024 / kStageBytes) : 24;
+  static constexpr int kStages = kStagesRaw / kMmaWarps * kMmaWarps;   // a stage is always consumed by the same MMA warp
+  static constexpr int kAccs = kMmaWarps;   // one accumulator per MMA-issuing warp, summed in the epilogue
+  static constexpr int kTmemCols = kAccs * BN < 32 ? 32 : kAccs * BN;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 512 /*barriers*/;
 };
 
 // phase timestamps of CTA 0 (globaltimer ns), written when dbg & 4: microbenchmark instrumentation only
@@ -39,11 +46,11 @@ __device__ __forceinline__ unsigned long long gtime() {
 }
 #define GEMM_TS(i) do { if ((dbg & 4) && blockIdx.x == 0 && blockIdx.y == 0) g_gemm_ts[i] = gtime(); } while (0)
 
-template <int BN, int EPI>
+template <int BM, int BN, int EPI>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_tc_kernel(const __grid_constant__ TensorMap tmA, const __grid_constant__ TensorMap tmB, int rows, int K,
                     EpiParams P, int dbg) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BM, BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
@@ -52,7 +59,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ TensorMap tmA, const __grid_constant
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_ready + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n0 = blockIdx.x * BN, m0 = blockIdx.y * kBM;
+  const int n0 = blockIdx.x * BN, m0 = blockIdx.y * BM;
   const int nkb = K / kBK;
   if (threadIdx.x == 0) GEMM_TS(0);
 
@@ -60,7 +67,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ TensorMap tmA, const __grid_constant
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    mbar_init(acc_ready, 1);
+    mbar_init(acc_ready, kMmaWarps);
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
@@ -77,7 +84,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ TensorMap tmA, const __grid_constant
       // waiting for its output, so the weight stream overlaps the predecessor's tail.
       const int pre = nkb < Cfg::kStages ? nkb : Cfg::kStages;
       // dbg (microbenchmarks only): bit 0 skips the activation loads, bit 1 the weight loads
-      const uint32_t tx = ((dbg & 1) ? 0 : kBM * kBK * 2) + ((dbg & 2) ? 0 : BN * kBK * 2);
+      const uint32_t tx = ((dbg & 1) ? 0 : BM * kBK * 2) + ((dbg & 2) ? 0 : BN * kBK * 2);
       for (int kb = 0; kb < pre; ++kb) {
         if (tx) mbar_expect_tx(&full[kb], tx); else mbar_arrive(&full[kb]);
         if (!(dbg & 2)) tma_load_2d_hint(smem + kb * Cfg::kStageBytes + Cfg::kABytes, &tmB, &full[kb], kb * kBK, n0, kEvictFirst);
@@ -96,63 +103,82 @@ gemm_bf16_tc_kernel(const __grid_constant__ TensorMap tmA, const __grid_constant
         if (!(dbg & 2)) tma_load_2d_hint(a + Cfg::kABytes, &tmB, &full[s], kb * kBK, n0, kEvictFirst);
       }
     }
-  } else if (warp == 1) {
+  } else if (warp <= kMmaWarps) {
+    // Two issuing threads: a single thread sustains only ~1 tcgen05.mma per 75 cycles (measured, independent of the tile
+    // shape), well below what the tensor pipe accepts for these narrow tiles.  dbg & 16 routes everything through warp 1.
+    const int j = warp - 1;
+    const bool solo = (dbg & 16) != 0;
     if (elect_one()) {
-      constexpr uint32_t idesc = umma_idesc_bf16(kBM, BN);
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % Cfg::kStages, it = kb / Cfg::kStages;
-        mbar_wait(&full[s], it & 1);
-        if (kb == 0) GEMM_TS(4);
-        tc_fence_after();
-        const uint32_t a_addr = smem_u32(smem + s * Cfg::kStageBytes);
-        const uint64_t adesc = umma_desc_sw128(a_addr), bdesc = umma_desc_sw128(a_addr + Cfg::kABytes);
+      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+      const uint32_t acc = tmem_acc + (solo ? 0 : j * BN);
+      bool first = true;
+      if (!(solo && j > 0)) {
+        for (int kb = solo ? 0 : j; kb < nkb; kb += solo ? 1 : kMmaWarps) {
+          const int s = kb % Cfg::kStages, it = kb / Cfg::kStages;
+          mbar_wait(&full[s], it & 1);
+          if (kb == 0) GEMM_TS(4);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + s * Cfg::kStageBytes);
+          const uint64_t adesc = umma_desc_sw128(a_addr), bdesc = umma_desc_sw128(a_addr + Cfg::kABytes);
 #pragma unroll
-        for (int k = 0; k < kBK / 16; ++k)  // +32 bytes along K inside the swizzle row = +2 in the address field
-          umma_bf16(tmem_acc, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
-        umma_commit(&empty[s]);             // frees the smem stage once these MMAs retire
+          for (int k = 0; k < kBK / 16; ++k)  // +32 bytes along K inside the swizzle row = +2 in the address field
+            umma_bf16(acc, adesc + 2 * k, bdesc + 2 * k, idesc, !(first && k == 0));
+          first = false;
+          umma_commit(&empty[s]);             // frees the smem stage once these MMAs retire
+        }
       }
       umma_commit(acc_ready);
-      GEMM_TS(5);
+      if (j == 0) GEMM_TS(5);
     }
   } else {
     const int quad = warp & 3;              // TMEM lanes [32*quad, 32*quad+32) are the ones this warp may read
-    const int r = m0 + quad * 32 + lane;
+    const int r = BM == 128 ? m0 + quad * 32 + lane : (lane < 16 ? m0 + quad * 16 + lane : 0x7fffffff);
+    const int n_acc = (dbg & 16) ? 1 : (nkb < kMmaWarps ? nkb : kMmaWarps);
     pdl_wait();                             // the epilogue reads predecessor outputs (residual, position)
     mbar_wait(acc_ready, 0);
-    if (threadIdx.x == 64) GEMM_TS(6);
+    if (threadIdx.x == 32 * (1 + kMmaWarps)) GEMM_TS(6);
     tc_fence_after();
 #pragma unroll
     for (int c = 0; c < BN; c += 16) {
       float v[16];
       tmem_ld16(tmem_acc + (static_cast<uint32_t>(quad * 32) << 16) + c, v);
+#pragma unroll
+      for (int a = 1; a < Cfg::kAccs; ++a) {
+        if (a < n_acc) {                    // warp-uniform
+          float u[16];
+          tmem_ld16(tmem_acc + (static_cast<uint32_t>(quad * 32) << 16) + a * BN + c, u);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] += u[i];
+        }
+      }
       if (r < rows) {
         epi8<EPI, __nv_bfloat16>(r, n0 + c, v, P);
         epi8<EPI, __nv_bfloat16>(r, n0 + c + 8, v + 8, P);
       }
     }
   }
-  if (threadIdx.x == 64) GEMM_TS(7);
+  if (threadIdx.x == 32 * (1 + kMmaWarps)) GEMM_TS(7);
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc<Cfg::kTmemCols>(tmem_acc);
   if (threadIdx.x == 32) GEMM_TS(8);
 }
 
-template <int BN, int EPI>
+template <int BM, int BN, int EPI>
 static int launch_tc(const void* x, const void* w, int rows, int N, int K, const EpiParams& P, cudaStream_t st) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BM, BN>;
   TensorMap tmA, tmB;
-  int rc = make_tmap_bf16_2d(&tmA, x, (uint64_t)rows, (uint64_t)K, (uint64_t)K * 2, kBM, kBK, true);
+  int rc = make_tmap_bf16_2d(&tmA, x, (uint64_t)rows, (uint64_t)K, (uint64_t)K * 2, BM, kBK, true);
   if (rc) return rc;
   rc = make_tmap_bf16_2d(&tmB, w, (uint64_t)N, (uint64_t)K, (uint64_t)K * 2, BN, kBK, true);
   if (rc) return rc;
-  auto kern = gemm_bf16_tc_kernel<BN, EPI>;
+  auto kern = gemm_bf16_tc_kernel<BM, BN, EPI>;
   static bool attr_set = false;
   if (!attr_set) {
     VLG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_set = true;
   }
-  dim3 grid(N / BN, (rows + kBM - 1) / kBM);
+  dim3 grid(N / BN, (rows + BM - 1) / BM);
   static const int dbg = [] { const char* e = getenv("VLG_GEMM_DEBUG"); return e ? atoi(e) : 0; }();
   VLG_CUDA(launch_kernel(kern, grid, dim3(kGemmThreads), Cfg::kSmemBytes, st, tmA, tmB, rows, K, P, dbg));
   VLG_LAUNCH_CHECK();
@@ -217,19 +243,35 @@ static int launch_f32(const void* x, const void* w, int rows, int N, int K, cons
 }
 
 // ============================================================================ dispatch
-// Tile width per problem: enough CTAs to pull the weight stream with all SMs, as few as possible
-// beyond that (every CTA re-reads the whole activation matrix from L2).
+// Tile shape per problem, by a small cost model measured on B200 (tools/gemm_phases.py): a CTA costs ~1.9 us of fixed
+// work (barriers, TMEM, first TMA round trip, epilogue) plus, per 64-wide k-block, the time to pull its activation and
+// weight tiles through the SM's L2 port (~116 GB/s); CTAs beyond one per SM run as a second wave.
 template <int EPI>
 static int launch_tc_auto(const void* x, const void* w, int rows, int N, int K, const EpiParams& P, cudaStream_t st) {
-  if constexpr (EPI == EPI_STORE) {   // tile-width override for microbenchmarks (plain-store epilogue only)
-    static const int bn = [] { const char* e = getenv("VLG_GEMM_BN"); return e ? atoi(e) : 0; }();
-    if (bn == 16) return launch_tc<16, EPI>(x, w, rows, N, K, P, st);
-    if (bn == 32) return launch_tc<32, EPI>(x, w, rows, N, K, P, st);
-    if (bn == 64 && N % 64 == 0) return launch_tc<64, EPI>(x, w, rows, N, K, P, st);
-    if (bn == 128 && N % 128 == 0) return launch_tc<128, EPI>(x, w, rows, N, K, P, st);
-  }
-  if (N % 32 == 0 && N / 32 >= 96) return launch_tc<32, EPI>(x, w, rows, N, K, P, st);
-  return launch_tc<16, EPI>(x, w, rows, N, K, P, st);
+  static const int force_bn = [] { const char* e = getenv("VLG_GEMM_BN"); return e ? atoi(e) : 0; }();
+  static const int force_bm = [] { const char* e = getenv("VLG_GEMM_BM"); return e ? atoi(e) : 0; }();
+  const int sms = num_sms(), nkb = K / kBK;
+  int best_bm = 128, best_bn = 16;
+  double best_t = 1e30;
+  const int bms[2] = {128, 64}, bns[4] = {16, 32, 64, 128};
+  for (int bm : bms)
+    for (int bn : bns) {
+      if (N % bn) continue;
+      if (force_bn && bn != force_bn) continue;
+      if (force_bm && bm != force_bm) continue;
+      if (rows <= 64 && bm == 128 && !force_bm) continue;            // never pad to 128 rows when 64 lanes suffice
+      if (EPI == EPI_SWIGLU && bn < 16) continue;
+      const long ctas = (long)(N / bn) * ((rows + bm - 1) / bm);
+      const double waves = (double)((ctas + sms - 1) / sms);
+      const double t = waves * (1.9 + nkb * (bm * 128.0 + bn * 128.0) / 116e3);
+      if (t < best_t - 1e-9) { best_t = t; best_bm = bm; best_bn = bn; }
+    }
+#define VLG_TC_CASE(BM_, BN_) if (best_bm == BM_ && best_bn == BN_) return launch_tc<BM_, BN_, EPI>(x, w, rows, N, K, P, st)
+  VLG_TC_CASE(128, 16); VLG_TC_CASE(128, 32); VLG_TC_CASE(128, 64); VLG_TC_CASE(128, 128);
+  VLG_TC_CASE(64, 16); VLG_TC_CASE(64, 32); VLG_TC_CASE(64, 64); VLG_TC_CASE(64, 128);
+#undef VLG_TC_CASE
+  set_error("gemm(bf16): no tile shape for N=%d", N);
+  return VLG_ERR_ARG;
 }
 
 int launch_gemm(int dtype, int epi, const void* x, const void* w, int rows, int N, int K, const EpiParams& P,
