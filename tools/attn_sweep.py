@@ -20,18 +20,23 @@ scratch = torch.empty(nb, dtype=torch.uint8, device=dev)
 st = torch.cuda.Stream()
 lib = L.lib()
 with torch.cuda.stream(st):
+    def call(pos, r):
+        L.check(lib.vlg_attn_decode(L.ptr(q), L.ptr(ks[r]), L.ptr(vs[r]), L.ptr(out), rows, H, D, S_max, pos, None, 0,
+                                    L.VLG_BF16, impl, L.ptr(scratch), nb, L.stream()))
+    call(0, 0)
+    st.synchronize()
     for pos in (0, 31, 63, 127, 191, 255, 319, 383, 447, 511, 575):
-        for r in range(3):
-            L.check(lib.vlg_attn_decode(L.ptr(q), L.ptr(ks[r]), L.ptr(vs[r]), L.ptr(out), rows, H, D, S_max, pos, None, 0,
-                                        L.VLG_BF16, impl, L.ptr(scratch), nb, L.stream()))
+        # replay a CUDA graph of 60 launches: the host launch rate (~11 us per ctypes call) must not pollute the timing
+        reps = 60
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr, stream=st):
+            for i in range(reps):
+                call(pos, i % regions)
+        gr.replay()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         st.synchronize()
         e0.record(st)
-        reps = 60
-        for i in range(reps):
-            r = i % regions
-            L.check(lib.vlg_attn_decode(L.ptr(q), L.ptr(ks[r]), L.ptr(vs[r]), L.ptr(out), rows, H, D, S_max, pos, None, 0,
-                                        L.VLG_BF16, impl, L.ptr(scratch), nb, L.stream()))
+        gr.replay()
         e1.record(st)
         st.synchronize()
         us = e0.elapsed_time(e1) * 1e3 / reps
