@@ -24,6 +24,8 @@ import sys
 import threading
 import time
 
+os.environ.setdefault("NCCL_DEBUG", "WARN")   # keep NCCL's version banner off stdout: the contract is ONE JSON line
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 for p in (ROOT, os.path.join(ROOT, "video-llamagen_b200")):
     if p not in sys.path:
@@ -306,7 +308,7 @@ def run_vlg(args):
                 "config": workload_config(world), "clocks": clocks,
                 "e2e": {"value": round(tokens_per_step * args.steps / e2e_s, 1), "unit": UNIT,
                         "h2d_bytes_per_step": B_LOCAL * 8 * world, "d2h_bytes_per_step": B_LOCAL * NEW_TOKENS * 4 * world},
-                "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu}
+                "gpu_launches": int(launches) * world, "roofline": roof, "cpu_baseline": cpu}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

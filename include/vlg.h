@@ -155,7 +155,9 @@ int vlg_forward_pos(vlg_ctx* ctx, const int64_t* tokens_dev, const int64_t* labe
                     int pos, float* logits_dev, void* hidden_dev, void* stream);
 
 /* Caption / latent projection MLP fc2(gelu_tanh(fc1 x)) (gpt.py:118-131): which = 0 cap_proj,
- * 1 vae_latent_adapter, 2 vae_latent_adapter2.  x_dev dtype [n, in], out_dev dtype [n, out]. */
+ * 1 vae_latent_adapter, 2 vae_latent_adapter2.  x_dev dtype [n, in], out_dev dtype [n, out].
+ * bf16 only: `in` is rounded up to a multiple of 64 and `out` to a multiple of 16 (tensor-core tile granularity): the
+ * caller zero-pads x / fc1 columns and fc2 rows / out columns accordingly (only the 8-wide t2v adapter ends are affected). */
 int vlg_mlp(vlg_ctx* ctx, int which, const void* x_dev, void* out_dev, int n, void* stream);
 
 /* The whole of generate() for c2i / t2i with device-resident inputs (generate.py:127-180):

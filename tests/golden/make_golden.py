@@ -115,14 +115,14 @@ def t2v_tiny(refv):
     gv = refv.gpt_video
     torch.manual_seed(9)
     args = gv.ModelArgs(dim=128, n_layer=2, n_head=2, vocab_size=64, block_size=16, multiple_of=64,
-                        cls_token_num=120, caption_dim=32, model_type="t2v", vae_embed_dim=8, num_frames=5,
+                        cls_token_num=120, caption_dim=64, model_type="t2v", vae_embed_dim=8, num_frames=5,
                         t_downsample_size=4, shuffle_video_tokens=False)
     model = gv.Transformer(args).eval()
     for n, p in model.named_parameters():
         if "vae_latent_adapter" in n or "cap_proj.fc2" in n:
             torch.nn.init.normal_(p, std=0.3)
     g = torch.Generator().manual_seed(13)
-    cond = torch.randn(2, 120, 32, generator=g)
+    cond = torch.randn(2, 120, 64, generator=g)
     emb_masks = torch.zeros(2, 120)
     emb_masks[0, 20:] = 1
     emb_masks[1, 113:] = 1

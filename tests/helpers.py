@@ -15,5 +15,5 @@ TINY_C2I = O.Geometry(dim=128, n_layer=2, n_head=2, vocab_size=512, block_size=1
 TINY_T2I = O.Geometry(dim=128, n_layer=2, n_head=2, vocab_size=256, block_size=16, multiple_of=64,
                       cls_token_num=120, caption_dim=32, model_type="t2i")
 TINY_T2V = O.Geometry(dim=128, n_layer=2, n_head=2, vocab_size=64, block_size=16, multiple_of=64,
-                      cls_token_num=120, caption_dim=32, model_type="t2v", vae_embed_dim=8, num_frames=5,
+                      cls_token_num=120, caption_dim=64, model_type="t2v", vae_embed_dim=8, num_frames=5,
                       t_downsample_size=4)

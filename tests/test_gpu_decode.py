@@ -156,3 +156,41 @@ def test_gptl_cfg2_full_size_bf16():
     rms_ours = (ours - truth).pow(2).mean().sqrt().item()
     rms_ref = (ref - truth).pow(2).mean().sqrt().item()
     assert rms_ours <= 1.5 * rms_ref + 1e-4, (rms_ours, rms_ref)       # no noisier than the reference's own bf16 run
+
+
+def test_t2v_tiny_trunk_adapters_3d_rope(golden):
+    """BASELINE cfg-4 path at fixture size: 120-token masked caption prefix, CFG row doubling, latent adapters in/out,
+    3D RoPE table, continuous-latent output (gpt_video.py:403-431) -- fp32 against the reference fixture, then bf16
+    (zero-padded adapter ends on the tensor cores) against the fp32 result."""
+    from vlg.gpt_video import Transformer as VT, ModelArgs as VArgs
+    f = golden("t2v_tiny.npz")
+    args = VArgs(dim=128, n_layer=2, n_head=2, vocab_size=64, block_size=16, multiple_of=64, cls_token_num=120,
+                 caption_dim=64, model_type="t2v", vae_embed_dim=8, num_frames=5, t_downsample_size=4,
+                 shuffle_video_tokens=False)
+    args.caption_dim = f["w.cls_embedding.cap_proj.fc1.weight"].shape[1]
+    m = VT(args).eval()
+    m.load_state_dict({k[2:]: torch.from_numpy(f[k]) for k in f.files if k.startswith("w.")}, strict=True)
+    assert torch.equal(m.freqs_cis, torch.from_numpy(f["rope"]))
+    cond = torch.from_numpy(f["cond"])
+    masks = torch.from_numpy(f["emb_masks"])
+    lat = torch.from_numpy(f["latents"])
+    N, T = lat.shape[1] + 1, 120
+
+    def run(model, dt):
+        model = model.to(DEV, dt)
+        rows = torch.cat([cond, torch.zeros_like(cond) + model.cls_embedding.uncond_embedding.float().cpu()]).to(DEV, dt)
+        model.setup_caches(4, T + N, None)
+        model.set_prefix_mask(torch.cat([masks, masks]))
+        out = [model(cond_embed=rows, input_pos=torch.arange(T, device=DEV))[0][:, -1]]
+        for i in range(N - 1):
+            x = torch.cat([lat[:, i:i + 1], lat[:, i:i + 1]]).to(DEV, dt)
+            out.append(model(video_latent=x, input_pos=torch.tensor([T + i], device=DEV))[0][:, -1])
+        return torch.stack(out).float()
+
+    o32 = run(m, torch.float32)
+    assert np.abs(o32.cpu().numpy() - f["out"]).max() < 1e-4
+    if f["w.cls_embedding.cap_proj.fc1.weight"].shape[1] % 64 == 0:
+        o16 = run(m, torch.bfloat16)
+        # bf16 end to end (weights, activations, cache) vs fp32: relative to the latent scale (|o| ~ 10 in this fixture)
+        assert (o16 - o32).abs().max() < 0.03 * o32.abs().max()
+        assert (o16 - o32).pow(2).mean().sqrt() < 0.01 * o32.pow(2).mean().sqrt()

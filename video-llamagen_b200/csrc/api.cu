@@ -321,6 +321,10 @@ extern "C" int vlg_mlp(vlg_ctx* c, int which, const void* x_dev, void* out_dev, 
     default: set_error("vlg_mlp: which=%d", which); return VLG_ERR_ARG;
   }
   VLG_REQUIRE(fc1 && fc2, "vlg_mlp: weights for MLP %d not provided", which);
+  if (g.dtype == VLG_BF16) {   // tcgen05 tile granularity: K %% 64, N %% 16 -- narrow adapter ends are zero-padded by the caller
+    in = (in + 63) / 64 * 64;
+    outw = (outw + 15) / 16 * 16;
+  }
   VLG_REQUIRE((size_t)n <= (size_t)c->max_rows * g.cls_token_num, "vlg_mlp: n=%d exceeds the staging buffer", n);
   cudaStream_t st = (cudaStream_t)stream;
   EpiParams P1{};

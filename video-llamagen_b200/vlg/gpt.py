@@ -192,10 +192,11 @@ class Engine:
         w.tok_embeddings = dev(model.tok_embeddings.weight)
         if model.model_type == 'c2i':
             w.cls_table = dev(model.cls_embedding.embedding_table.weight)
-        else:
+        elif isinstance(model.cls_embedding, CaptionEmbedder):
             w.cap_fc1 = dev(model.cls_embedding.cap_proj.fc1.weight)
             w.cap_fc2 = dev(model.cls_embedding.cap_proj.fc2.weight)
             self.uncond = model.cls_embedding.uncond_embedding.detach().to(self.device, self.dtype).contiguous()
+        self._extra_weights(model, w, dev)
         w.norm = dev(model.norm.weight)
         w.output = dev(model.output.weight)
         w.rope_table = table.data_ptr()
@@ -211,6 +212,9 @@ class Engine:
             L.check(lib.vlg_ctx_create(C.byref(self.geo), C.byref(w), self.max_rows, self.max_seq, C.c_void_p(base),
                                        nbytes, C.byref(self.ctx)))
         self.rows = 0
+
+    def _extra_weights(self, model, w, dev):
+        """Hook for model variants with more projections (vlg.gpt_video)."""
 
     def __del__(self):
         try:
