@@ -28,8 +28,8 @@ size_t align_up(size_t v, size_t a = 1024) { return (v + a - 1) / a * a; }
 int round8(int n) { return (n + 7) / 8 * 8; }
 
 struct Layout {
-  size_t k_cache, v_cache, h, xn, q, attn, ffn, logits, attn_scratch, state, mask, seq, labels, cond_rows, prefix_emb,
-      mlp_tmp, total;
+  size_t k_cache, v_cache, h, xn, q, attn, ffn, logits, attn_scratch, state, norm_flags, mask, seq, labels, cond_rows,
+      prefix_emb, mlp_tmp, total;
 };
 
 Layout make_layout(const vlg_geometry& g, int max_rows, int max_seq) {
@@ -49,6 +49,7 @@ Layout make_layout(const vlg_geometry& g, int max_rows, int max_seq) {
   L.logits = take((size_t)max_rows * (g.vocab_size > 0 ? g.vocab_size : 1) * 4);
   L.attn_scratch = take(attn_scratch_bytes(max_rows, g.n_head, D, S));
   L.state = take(sizeof(StepState));
+  L.norm_flags = take((size_t)(2 * g.n_layer + 1) * sizeof(unsigned));   // fused-RMSNorm arrival counters, one per norm
   L.mask = take((size_t)max_rows * g.cls_token_num);
   L.seq = take((size_t)max_rows * S * sizeof(int32_t));
   L.labels = take((size_t)max_rows * sizeof(int64_t));
@@ -74,6 +75,7 @@ struct vlg_ctx {
   int rows = 0;
   bool has_mask = false;
   bool force_generic_attn = false;   // VLG_ATTN=generic: A/B the two attention kernels
+  bool no_fused_norm = true;         // VLG_FUSED_NORM=1 enables the fused RMSNorm prologue of the GEMMs (A/B)
   // graph capture is illegal on the legacy default stream (torch's default): such callers are forked onto this one
   cudaStream_t own_stream = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
@@ -118,8 +120,10 @@ __global__ void take_prefix_kernel(const T* __restrict__ emb, T* __restrict__ h,
   for (int i = threadIdx.x; i < dim * (int)sizeof(T) / 16; i += blockDim.x) dst[i] = src[i];
 }
 
-// N transformer blocks on ctx->h (in place); final-normed hidden left in ctx->xn.
-int run_trunk(vlg_ctx* c, const int* pos_ptr, int pos_imm, int max_pos, cudaStream_t st) {
+// N transformer blocks on ctx->h (in place).  bf16: the RMSNorms are fused into the consuming tensor-core GEMMs (the first
+// CTAs of the GEMM normalise h into xn, everyone waits on an arrival counter); the final norm is fused into the head GEMM
+// when `fuse_final` is set, otherwise (and in fp32) it is a separate launch that leaves the normed hidden in ctx->xn.
+int run_trunk(vlg_ctx* c, const int* pos_ptr, int pos_imm, int max_pos, bool fuse_final, cudaStream_t st) {
   const vlg_geometry& g = c->g;
   const int R = c->rows, d = g.dim, hid = g.hidden_dim;
   void* h = c->at<void>(c->L.h);
@@ -127,14 +131,21 @@ int run_trunk(vlg_ctx* c, const int* pos_ptr, int pos_imm, int max_pos, cudaStre
   void* q = c->at<void>(c->L.q);
   void* attn = c->at<void>(c->L.attn);
   void* ffn = c->at<void>(c->L.ffn);
+  unsigned* flags = c->at<unsigned>(c->L.norm_flags);
+  const bool fuse = g.dtype == VLG_BF16 && !c->no_fused_norm;
+  if (fuse) VLG_CUDA(cudaMemsetAsync(flags, 0, (size_t)(2 * g.n_layer + 1) * sizeof(unsigned), st));
+  auto with_norm = [&](EpiParams& P, const void* weight, int idx) {
+    P.norm_src = h; P.norm_weight = weight; P.norm_dst = xn; P.norm_flag = flags + idx; P.norm_eps = g.norm_eps;
+  };
   int rc;
   for (int l = 0; l < g.n_layer; ++l) {
     const vlg_layer_weights& lw = c->layers[l];
-    if ((rc = launch_rmsnorm(g.dtype, h, lw.attention_norm, xn, R, d, g.norm_eps, st))) return rc;
     EpiParams P{};
     P.q_out = q; P.k_cache = c->kc(l); P.v_cache = c->vc(l);
     P.rope = c->w.rope_table; P.pos_ptr = pos_ptr; P.pos_imm = pos_imm;
     P.S_max = c->S_max; P.H = g.n_head; P.D = c->D; P.dim = d;
+    if (fuse) with_norm(P, lw.attention_norm, 2 * l);
+    else if ((rc = launch_rmsnorm(g.dtype, h, lw.attention_norm, xn, R, d, g.norm_eps, st))) return rc;
     if ((rc = launch_gemm(g.dtype, EPI_QKV_ROPE, xn, lw.wqkv, R, 3 * d, d, P, st))) return rc;
     AttnArgs a{};
     a.q = q; a.k_cache = c->kc(l); a.v_cache = c->vc(l); a.out = attn;
@@ -149,21 +160,27 @@ int run_trunk(vlg_ctx* c, const int* pos_ptr, int pos_imm, int max_pos, cudaStre
     EpiParams Po{};
     Po.out = h; Po.ld_out = d; Po.resid = h;
     if ((rc = launch_gemm(g.dtype, EPI_RESID, attn, lw.wo, R, d, d, Po, st))) return rc;
-    if ((rc = launch_rmsnorm(g.dtype, h, lw.ffn_norm, xn, R, d, g.norm_eps, st))) return rc;
     EpiParams Pf{};
     Pf.out = ffn; Pf.ld_out = hid;
+    if (fuse) with_norm(Pf, lw.ffn_norm, 2 * l + 1);
+    else if ((rc = launch_rmsnorm(g.dtype, h, lw.ffn_norm, xn, R, d, g.norm_eps, st))) return rc;
     if ((rc = launch_gemm(g.dtype, EPI_SWIGLU, xn, lw.w13, R, 2 * hid, d, Pf, st))) return rc;
     EpiParams P2{};
     P2.out = h; P2.ld_out = d; P2.resid = h;
     if ((rc = launch_gemm(g.dtype, EPI_RESID, ffn, lw.w2, R, d, hid, P2, st))) return rc;
   }
+  if (fuse && fuse_final) return VLG_OK;
   return launch_rmsnorm(g.dtype, h, c->w.norm, xn, R, d, g.norm_eps, st);
 }
 
-int run_head(vlg_ctx* c, float* logits, cudaStream_t st) {
+int run_head(vlg_ctx* c, float* logits, bool fused_final_norm, cudaStream_t st) {
   EpiParams P{};
   P.out = logits;
   P.ld_out = c->g.vocab_size;
+  if (fused_final_norm && c->g.dtype == VLG_BF16 && !c->no_fused_norm) {
+    P.norm_src = c->at<void>(c->L.h); P.norm_weight = c->w.norm; P.norm_dst = c->at<void>(c->L.xn);
+    P.norm_flag = c->at<unsigned>(c->L.norm_flags) + 2 * c->g.n_layer; P.norm_eps = c->g.norm_eps;
+  }
   return launch_gemm(c->g.dtype, EPI_STORE_F32, c->at<void>(c->L.xn), c->w.output, c->rows, c->g.vocab_size, c->g.dim, P, st);
 }
 
@@ -197,8 +214,8 @@ int decode_step(vlg_ctx* c, const vlg_generate_params& p, cudaStream_t st) {
                          c->at<int32_t>(c->L.seq), p.max_new_tokens, &c->state()->step, -1, nullptr, p.B, 0,
                          g.vocab_size, st);
   if (rc) return rc;
-  if ((rc = run_trunk(c, &c->state()->pos, 0, g.cls_token_num + p.max_new_tokens - 1, st))) return rc;
-  if ((rc = run_head(c, c->at<float>(c->L.logits), st))) return rc;
+  if ((rc = run_trunk(c, &c->state()->pos, 0, g.cls_token_num + p.max_new_tokens - 1, true, st))) return rc;
+  if ((rc = run_head(c, c->at<float>(c->L.logits), true, st))) return rc;
   return launch_sample(loop_sample_args(c, p), st);
 }
 
@@ -241,6 +258,10 @@ extern "C" int vlg_ctx_create(const vlg_geometry* g, const vlg_weights* w, int m
   c->L = L;
   const char* env = getenv("VLG_ATTN");
   c->force_generic_attn = env && strcmp(env, "generic") == 0;
+  // Fused RMSNorm prologue is opt-in (VLG_FUSED_NORM=1): measured 985 ms vs 939 ms per cfg-2 generate() -- the in-kernel
+  // flag hand-off costs as much latency as the kernel boundary it removes.
+  const char* fn = getenv("VLG_FUSED_NORM");
+  c->no_fused_norm = !(fn && fn[0] == '1');
   VLG_CUDA(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
   VLG_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
   VLG_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
@@ -297,13 +318,14 @@ extern "C" int vlg_forward_pos(vlg_ctx* c, const int64_t* tokens_dev, const int6
                              cudaMemcpyDeviceToDevice, st));
   }
   if (rc) return rc;
-  if ((rc = run_trunk(c, nullptr, pos, pos, st))) return rc;
+  const bool fuse_final = logits_dev != nullptr && hidden_dev == nullptr;   // the normed hidden is materialised only on request
+  if ((rc = run_trunk(c, nullptr, pos, pos, fuse_final, st))) return rc;
   if (hidden_dev)
     VLG_CUDA(cudaMemcpyAsync(hidden_dev, c->at<void>(c->L.xn), (size_t)c->rows * g.dim * esz(g.dtype),
                              cudaMemcpyDeviceToDevice, st));
   if (logits_dev) {
     VLG_REQUIRE(c->w.output && g.vocab_size > 0, "vlg_forward_pos: model has no output head");
-    if ((rc = run_head(c, logits_dev, st))) return rc;
+    if ((rc = run_head(c, logits_dev, fuse_final, st))) return rc;
   }
   return VLG_OK;
 }
@@ -384,7 +406,7 @@ static int generate_on(vlg_ctx* c, const vlg_generate_params* pp, const void* co
     if ((rc = launch_gather(g.dtype, c->w.cls_table, c->at<void>(c->L.h), rows, g.dim, nullptr, nullptr, 0, nullptr, 0,
                             static_cast<const int64_t*>(cond_dev), p.B, g.num_classes, g.num_classes + 1, st)))
       return rc;
-    if ((rc = run_trunk(c, &c->state()->pos, 0, T + N - 1, st))) return rc;
+    if ((rc = run_trunk(c, &c->state()->pos, 0, T + N - 1, true, st))) return rc;
   } else {
     VLG_REQUIRE(!cfg || uncond_dev, "vlg_generate: t2i with cfg_scale > 1 needs the uncond embedding");
     const size_t per_row = (size_t)T * g.caption_dim;
@@ -403,10 +425,10 @@ static int generate_on(vlg_ctx* c, const vlg_generate_params* pp, const void* co
       else
         take_prefix_kernel<float><<<rows, 128, 0, st>>>(c->at<float>(c->L.prefix_emb), c->at<float>(c->L.h), T, t, g.dim);
       VLG_LAUNCH_CHECK();
-      if ((rc = run_trunk(c, nullptr, t, T + N - 1, st))) return rc;
+      if ((rc = run_trunk(c, nullptr, t, T + N - 1, t == T - 1, st))) return rc;
     }
   }
-  if ((rc = run_head(c, c->at<float>(c->L.logits), st))) return rc;
+  if ((rc = run_head(c, c->at<float>(c->L.logits), true, st))) return rc;
   if ((rc = launch_sample(loop_sample_args(c, p), st))) return rc;   // step 0 -> 1, pos T-1 -> T
 
   // ---- decode loop (generate.py:105-124) as a replayed CUDA graph

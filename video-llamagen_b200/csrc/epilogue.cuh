@@ -28,6 +28,14 @@ struct EpiParams {
   const int* pos_ptr;   // device scalar with the cache slot, or nullptr -> pos_imm
   int pos_imm;
   int S_max, H, D, dim;
+  // Fused RMSNorm prologue (bf16 tensor-core GEMM only; norm_flag == nullptr -> the A operand is used as given).
+  // The first CTAs of the grid normalise `norm_src` into the A buffer (the tensor map's base) and publish a counter;
+  // every CTA's producer waits on it before loading A.  Same arithmetic as rmsnorm_kernel (gpt.py:143-148).
+  const void* norm_src;     // [rows, K] un-normalised hidden state
+  const void* norm_weight;  // [K]
+  void* norm_dst;           // [rows, K] = the buffer the A tensor map reads
+  unsigned* norm_flag;      // zero before the launch; CTAs that normalised rows add 1 each
+  float norm_eps;
 };
 
 template <typename T> __device__ __forceinline__ void store8(T* dst, const float* v);

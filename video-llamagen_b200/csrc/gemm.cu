@@ -46,12 +46,49 @@ __device__ __forceinline__ unsigned long long gtime() {
 }
 #define GEMM_TS(i) do { if ((dbg & 4) && blockIdx.x == 0 && blockIdx.y == 0) g_gemm_ts[i] = gtime(); } while (0)
 
+constexpr int kNormCtas = 64;       // CTAs that share the fused RMSNorm prologue (always the first ones dispatched)
+
+// RMSNorm of row r by the 128 epilogue threads (te = 0..127); bit-identical to rmsnorm_kernel<bf16> (same partial sums).
+__device__ __forceinline__ void fused_rmsnorm_row(const __nv_bfloat16* __restrict__ src, const __nv_bfloat16* __restrict__ w,
+                                                  __nv_bfloat16* __restrict__ dst, int K, float eps, int te, float* s_part) {
+  const int nvec = K / 8;
+  float v[4][8], g[4][8];
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int vi = te + i * 128;
+    if (vi < nvec) {
+      load8<__nv_bfloat16>(w + vi * 8, g[i]);
+      load8<__nv_bfloat16>(src + vi * 8, v[i]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) ss = __fadd_rn(ss, __fmul_rn(v[i][j], v[i][j]));
+    }
+  }
+  ss = warp_sum(ss);
+  asm volatile("bar.sync 2, 128;" ::: "memory");          // previous row's readers of s_part are done
+  if ((te & 31) == 0) s_part[te >> 5] = ss;
+  asm volatile("bar.sync 2, 128;" ::: "memory");
+  const float tot = ((s_part[0] + s_part[1]) + s_part[2]) + s_part[3];
+  const float rs = rsqrtf(__fdiv_rn(tot, (float)K) + eps);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int vi = te + i * 128;
+    if (vi < nvec) {
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = __fmul_rn(rnd<__nv_bfloat16>(__fmul_rn(v[i][j], rs)), g[i][j]);
+      store8<__nv_bfloat16>(dst + vi * 8, o);
+    }
+  }
+}
+
 template <int BM, int BN, int EPI>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_tc_kernel(const __grid_constant__ TensorMap tmA, const __grid_constant__ TensorMap tmB, int rows, int K,
                     EpiParams P, int dbg) {
   using Cfg = GemmCfg<BM, BN>;
   extern __shared__ uint8_t smem_raw[];
+  __shared__ float s_norm_part[4];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
   uint64_t* empty = full + Cfg::kStages;
@@ -91,6 +128,17 @@ gemm_bf16_tc_kernel(const __grid_constant__ TensorMap tmA, const __grid_constant
       }
       GEMM_TS(2);
       pdl_wait();
+      if (P.norm_flag != nullptr) {           // fused RMSNorm: A is being written by the first CTAs of this very grid
+        const unsigned total = gridDim.x * gridDim.y;
+        const unsigned need = total < (unsigned)kNormCtas ? total : (unsigned)kNormCtas;
+        uint32_t spins = 0;
+        unsigned seen;
+        do {
+          asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(P.norm_flag) : "memory");
+          if (++spins > (1u << 24)) { printf("vlg: fused rmsnorm flag timeout (block %d)\n", blockIdx.x); __trap(); }
+        } while (seen < need);
+        asm volatile("fence.proxy.async;" ::: "memory");   // generic-proxy writes of other SMs -> this SM's TMA reads
+      }
       GEMM_TS(3);
       for (int kb = 0; kb < pre; ++kb)
         if (!(dbg & 1)) tma_load_2d_hint(smem + kb * Cfg::kStageBytes, &tmA, &full[kb], kb * kBK, m0, kEvictLast);
@@ -135,6 +183,20 @@ gemm_bf16_tc_kernel(const __grid_constant__ TensorMap tmA, const __grid_constant
     const int r = BM == 128 ? m0 + quad * 32 + lane : (lane < 16 ? m0 + quad * 16 + lane : 0x7fffffff);
     const int n_acc = (dbg & 16) ? 1 : (nkb < kMmaWarps ? nkb : kMmaWarps);
     pdl_wait();                             // the epilogue reads predecessor outputs (residual, position)
+    if (P.norm_flag != nullptr) {
+      const unsigned total = gridDim.x * gridDim.y, bid = blockIdx.y * gridDim.x + blockIdx.x;
+      const unsigned n_norm = total < (unsigned)kNormCtas ? total : (unsigned)kNormCtas;
+      if (bid < n_norm) {
+        const int te = threadIdx.x - 32 * (1 + kMmaWarps);
+        for (int rr = bid; rr < rows; rr += n_norm)
+          fused_rmsnorm_row(static_cast<const __nv_bfloat16*>(P.norm_src) + (size_t)rr * K,
+                            static_cast<const __nv_bfloat16*>(P.norm_weight),
+                            static_cast<__nv_bfloat16*>(P.norm_dst) + (size_t)rr * K, K, P.norm_eps, te, s_norm_part);
+        __threadfence();
+        asm volatile("bar.sync 2, 128;" ::: "memory");
+        if (te == 0) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(P.norm_flag) : "memory");
+      }
+    }
     mbar_wait(acc_ready, 0);
     if (threadIdx.x == 32 * (1 + kMmaWarps)) GEMM_TS(6);
     tc_fence_after();
