@@ -22,10 +22,39 @@ constexpr int kCW = 8;                      // consumer warps
 constexpr int kStagesA = 16;                // ring depth (multiple of kCW: stage s always belongs to warp s % kCW)
 constexpr int kTileBytes = kTile * 128;     // one K or V tile (D = 64 bf16 = 128 B per position)
 constexpr int kStageBytesA = 2 * kTileBytes;
-constexpr int kAttnTmaThreads = (kCW + 1) * 32;
+constexpr int kAttnTmaThreads = (kCW + 2) * 32;     // consumers, TMA producer (warp kCW), merger (warp kCW + 1)
 constexpr int kMaxSplitsT = 32;
 
 constexpr int kSlots = 16;                  // in-flight work items per CTA whose partial states await their merge
+
+// Explicit shared-space accesses: the ring lives behind a manually aligned pointer, which makes the compiler fall back
+// to generic LD/ST (slower address-space resolution on every access) unless the state space is spelled out.
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 r;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
+  return r;
+}
+__device__ __forceinline__ float4 lds128f(uint32_t addr) {
+  float4 r;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(addr));
+  return r;
+}
+__device__ __forceinline__ void sts32f(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v)); }
+
+// CTA-scope synchronisation on shared-memory words (generic-address atomics would take the global atomic path)
+__device__ __forceinline__ unsigned smem_atom_add_acq_rel(volatile unsigned* p, unsigned v) {
+  unsigned old;
+  asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(smem_u32(const_cast<unsigned*>(p))), "r"(v) : "memory");
+  return old;
+}
+__device__ __forceinline__ unsigned smem_ld_acquire(const volatile unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(const_cast<const unsigned*>(p))) : "memory");
+  return v;
+}
+__device__ __forceinline__ void smem_st_release(volatile unsigned* p, unsigned v) {
+  asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"(smem_u32(const_cast<unsigned*>(p))), "r"(v) : "memory");
+}
 
 struct ItemSlot { float m, l, pad0, pad1; float o[64]; };
 
@@ -34,7 +63,7 @@ struct AttnTmaSmem {
   ItemSlot slot[kSlots][kCW];
   float p[kCW][kTile];
   uint64_t full[kStagesA], empty[kStagesA];
-  unsigned cnt[kSlots];                     // warps that have published their partial for the item in this slot
+  volatile unsigned cnt[kSlots];            // warps that have published their partial for the item in this slot
   volatile unsigned gen[kSlots];            // how many items have been merged out of this slot (slot reuse gate)
 };
 
@@ -85,8 +114,60 @@ attn_decode_tma_kernel(const __grid_constant__ TensorMap tmK, const __grid_const
     return;
   }
 
+  if (warp == kCW + 1) {
+    // ------------------------------------------------------------------ merger
+    // Folds the consumers' partial (m, l, o) states of each multi-warp item and writes the output, so that no consumer
+    // ever stalls its tile stream on merge work (otherwise the slowest warp of every item also pays for the merge).
+    uint32_t gtm = 0;
+    int mi = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++mi) {
+      const int rh = item / n_splits, split = item - rh * n_splits;
+      const int s_begin = split * chunk, s_end = min(n, s_begin + chunk);
+      const int n_tiles = s_end > s_begin ? (s_end - s_begin + kTile - 1) / kTile : 0;
+      const int w0 = (int)(gtm % kCW);
+      const int participants = n_tiles < kCW ? n_tiles : kCW;
+      gtm += n_tiles;
+      if (participants <= 1) continue;                                // finalised by its only consumer
+      const int sj = mi % kSlots;
+      const unsigned my_gen = (unsigned)(mi / kSlots);
+      if (lane == 0) {
+        uint32_t spins = 0;
+        while (smem_ld_acquire(&sm.cnt[sj]) != (unsigned)participants)
+          if (++spins > (1u << 26)) { printf("vlg: attention merge timeout\n"); __trap(); }
+      }
+      __syncwarp();
+      const ItemSlot* sl = sm.slot[sj];
+      float mm = -INFINITY;
+      for (int k = 0; k < participants; ++k) mm = fmaxf(mm, sl[(w0 + k) % kCW].m);
+      float lt = 0.f, o0 = 0.f, o1 = 0.f;
+      for (int k = 0; k < participants; ++k) {
+        const ItemSlot& ps = sl[(w0 + k) % kCW];
+        const float a = ps.m == -INFINITY ? 0.f : exp2f(ps.m - mm);
+        lt = fmaf(ps.l, a, lt);
+        const float2 ov = *reinterpret_cast<const float2*>(&ps.o[2 * lane]);
+        o0 = fmaf(ov.x, a, o0);
+        o1 = fmaf(ov.y, a, o1);
+      }
+      if (n_splits == 1) {
+        const float inv = 1.0f / lt;
+        *reinterpret_cast<uint32_t*>(out + (size_t)rh * 64 + 2 * lane) = pack_bf16(o0 * inv, o1 * inv);
+      } else {
+        float* pp = part + ((size_t)rh * n_splits + split) * 66;
+        *reinterpret_cast<float2*>(pp + 2 + 2 * lane) = make_float2(o0, o1);
+        if (lane == 0) { pp[0] = mm * 0.6931471805599453f; pp[1] = lt; }   // natural-log units for the combiner
+      }
+      __syncwarp();                                                   // all lanes are done with the slot
+      if (lane == 0) {
+        sm.cnt[sj] = 0;
+        smem_st_release(&sm.gen[sj], my_gen + 1);                     // hand the slot to item mi + kSlots
+      }
+    }
+    return;
+  }
+
   // -------------------------------------------------------------------- consumers
   const int g = lane >> 3, c = lane & 7;
+  const uint32_t ring_base = smem_u32(&sm.ring[0][0]), p_base = smem_u32(&sm.p[warp][0]);
   const float kScale = 0.125f * 1.4426950408889634f;   // 1/sqrt(64) * log2(e)
   uint32_t gt0 = 0;                                     // tiles issued before the current item
   int item_i = 0;
@@ -122,15 +203,15 @@ attn_decode_tma_kernel(const __grid_constant__ TensorMap tmK, const __grid_const
     for (int t = first_t; t < n_tiles; t += kCW) {
       const uint32_t gt = gt_item + t, st = gt % kStagesA, it = gt / kStagesA;
       mbar_wait(&sm.full[st], it & 1);
-      const uint8_t* kt = sm.ring[st];
-      const uint8_t* vt = kt + kTileBytes;
+      const uint32_t kt = ring_base + st * kStageBytesA;
+      const uint32_t vt = kt + kTileBytes;
       const int sidx = s_begin + t * kTile + lane;     // this lane's cache position
 
       // ---- scores: lane <-> position, 4 independent partial sums
       float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
 #pragma unroll
       for (int ch = 0; ch < 8; ++ch) {
-        const uint4 kk = *reinterpret_cast<const uint4*>(kt + lane * 128 + ((ch ^ (lane & 7)) << 4));
+        const uint4 kk = lds128(kt + lane * 128 + ((ch ^ (lane & 7)) << 4));
         d0 = fmaf(qf[8 * ch + 0], bf16lo(kk.x), d0); d1 = fmaf(qf[8 * ch + 1], bf16hi(kk.x), d1);
         d2 = fmaf(qf[8 * ch + 2], bf16lo(kk.y), d2); d3 = fmaf(qf[8 * ch + 3], bf16hi(kk.y), d3);
         d0 = fmaf(qf[8 * ch + 4], bf16lo(kk.z), d0); d1 = fmaf(qf[8 * ch + 5], bf16hi(kk.z), d1);
@@ -155,19 +236,19 @@ attn_decode_tma_kernel(const __grid_constant__ TensorMap tmK, const __grid_const
 #pragma unroll
       for (int i = 0; i < 8; ++i) acc[i] *= corr;
       __syncwarp();                                     // previous tile's readers of sm.p are done
-      sm.p[warp][lane] = p;
+      sts32f(p_base + lane * 4, p);
       __syncwarp();
 
       // ---- o += p . V : lane (g, c) covers rows 8g..8g+7, dims 8c..8c+7
-      const float4 pa = *reinterpret_cast<const float4*>(&sm.p[warp][8 * g]);
-      const float4 pb = *reinterpret_cast<const float4*>(&sm.p[warp][8 * g + 4]);
+      const float4 pa = lds128f(p_base + 32 * g);
+      const float4 pb = lds128f(p_base + 32 * g + 16);
       const float pj[8] = {pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, pb.w};
 #pragma unroll
       // Rows past the end of the prefix carry p = 0; their bytes are finite (the cache is zero-initialised once and only
       // ever holds finite values; TMA zero-fills out-of-bounds rows), so no branch is needed to keep them out.
       for (int j = 0; j < 8; ++j) {
         const int row = 8 * g + j;
-        const uint4 vv = *reinterpret_cast<const uint4*>(vt + row * 128 + ((c ^ (row & 7)) << 4));
+        const uint4 vv = lds128(vt + row * 128 + ((c ^ (row & 7)) << 4));
         acc[0] = fmaf(pj[j], bf16lo(vv.x), acc[0]); acc[1] = fmaf(pj[j], bf16hi(vv.x), acc[1]);
         acc[2] = fmaf(pj[j], bf16lo(vv.y), acc[2]); acc[3] = fmaf(pj[j], bf16hi(vv.y), acc[3]);
         acc[4] = fmaf(pj[j], bf16lo(vv.z), acc[4]); acc[5] = fmaf(pj[j], bf16hi(vv.z), acc[5]);
@@ -185,68 +266,42 @@ attn_decode_tma_kernel(const __grid_constant__ TensorMap tmK, const __grid_const
       acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 8);
       acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 16);
     }
-    const int sj = item_i % kSlots;
-    const unsigned my_gen = (unsigned)(item_i / kSlots);
-    if (lane == 0) {                                                  // slot reuse gate: previous occupant merged?
-      uint32_t spins = 0;
-      while (sm.gen[sj] != my_gen)
-        if (++spins > (1u << 26)) { printf("vlg: attention slot timeout\n"); __trap(); }
-    }
-    __syncwarp();
-    float o0 = 0.f, o1 = 0.f, lt = l, mm = m;
-    bool last = true;
     if (participants <= 1) {
-      // single-warp item: lane L needs dims 2L, 2L+1 = acc[(2L) % 8 (+1)] of a lane with c == L / 4
+      // single-warp item (or an empty split): finalise here; lane L needs dims 2L, 2L+1 = acc[(2L) % 8 (+1)] of lane L / 4
+      float o0 = 0.f, o1 = 0.f;
       const int src = lane >> 2, sel = (lane & 3) * 2;
 #pragma unroll
       for (int i = 0; i < 8; i += 2) {
         const float a0 = __shfl_sync(0xffffffffu, acc[i], src), a1 = __shfl_sync(0xffffffffu, acc[i + 1], src);
         if (sel == i) { o0 = a0; o1 = a1; }
       }
-    } else {
-      ItemSlot& pub = sm.slot[sj][warp];
-      if (lane == 0) { pub.m = m; pub.l = l; }
-      if (lane < 8) {
-        *reinterpret_cast<float4*>(&pub.o[8 * c]) = make_float4(acc[0], acc[1], acc[2], acc[3]);
-        *reinterpret_cast<float4*>(&pub.o[8 * c + 4]) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+      if (n_splits == 1) {
+        const float inv = 1.0f / l;
+        *reinterpret_cast<uint32_t*>(out + (size_t)rh * 64 + 2 * lane) = pack_bf16(o0 * inv, o1 * inv);
+      } else {
+        float* pp = part + ((size_t)rh * n_splits + split) * 66;
+        *reinterpret_cast<float2*>(pp + 2 + 2 * lane) = make_float2(o0, o1);
+        if (lane == 0) { pp[0] = m * 0.6931471805599453f; pp[1] = l; }
       }
-      __threadfence_block();
-      __syncwarp();
-      unsigned arrived = 0;
-      if (lane == 0) arrived = atomicAdd(&sm.cnt[sj], 1u);
-      arrived = __shfl_sync(0xffffffffu, arrived, 0);
-      last = arrived == (unsigned)participants - 1;
-      if (last) {
-        __threadfence_block();
-        const ItemSlot* sl = sm.slot[sj];
-        mm = -INFINITY;
-        for (int k = 0; k < participants; ++k) mm = fmaxf(mm, sl[(w0 + k) % kCW].m);
-        lt = 0.f;
-        for (int k = 0; k < participants; ++k) {
-          const ItemSlot& ps = sl[(w0 + k) % kCW];
-          const float a = ps.m == -INFINITY ? 0.f : exp2f(ps.m - mm);
-          lt = fmaf(ps.l, a, lt);
-          const float2 ov = *reinterpret_cast<const float2*>(&ps.o[2 * lane]);
-          o0 = fmaf(ov.x, a, o0);
-          o1 = fmaf(ov.y, a, o1);
-        }
-      }
+      continue;
     }
-    if (!last) continue;
-    if (n_splits == 1) {
-      const float inv = 1.0f / lt;
-      *reinterpret_cast<uint32_t*>(out + (size_t)rh * 64 + 2 * lane) = pack_bf16(o0 * inv, o1 * inv);
-    } else {
-      float* pp = part + ((size_t)rh * n_splits + split) * 66;
-      *reinterpret_cast<float2*>(pp + 2 + 2 * lane) = make_float2(o0, o1);
-      if (lane == 0) { pp[0] = mm * 0.6931471805599453f; pp[1] = lt; }   // natural-log units for the combiner
+    // multi-warp item: publish the partial state; the merger warp does the rest
+    const int sj = item_i % kSlots;
+    const unsigned my_gen = (unsigned)(item_i / kSlots);
+    if (lane == 0) {                                                  // slot reuse gate: previous occupant merged?
+      uint32_t spins = 0;
+      while (smem_ld_acquire(&sm.gen[sj]) != my_gen)
+        if (++spins > (1u << 26)) { printf("vlg: attention slot timeout\n"); __trap(); }
     }
-    __syncwarp();                                                     // all lanes are done with the slot
-    if (lane == 0) {
-      sm.cnt[sj] = 0;
-      __threadfence_block();
-      sm.gen[sj] = my_gen + 1;                                        // hand the slot to item_i + kSlots
+    __syncwarp();
+    ItemSlot& pub = sm.slot[sj][warp];
+    if (lane == 0) { pub.m = m; pub.l = l; }
+    if (lane < 8) {
+      *reinterpret_cast<float4*>(&pub.o[8 * c]) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+      *reinterpret_cast<float4*>(&pub.o[8 * c + 4]) = make_float4(acc[4], acc[5], acc[6], acc[7]);
     }
+    __syncwarp();                                                     // lanes' slot writes ordered before lane 0's release
+    if (lane == 0) smem_atom_add_acq_rel(&sm.cnt[sj], 1u);
   }
 }
 
