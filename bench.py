@@ -129,10 +129,16 @@ def attention_kernel_roofline(dev, rows, H, S_max, n_pos, peak_gbs, src):
         e1.record(st)
         st.synchronize()
     ms = e0.elapsed_time(e1)
+    traffic = None                                          # DRAM bytes per launch from the committed ncu capture
+    tpath = os.path.join(ROOT, "profiles", "r1_attention_traffic.json")
+    if os.path.exists(tpath) and (rows, H, n_pos) == (128, 16, 576):
+        t = json.load(open(tpath))
+        traffic = t["dram_bytes_read_per_launch"] + t["dram_bytes_write_per_launch"]
     bytes_total = sum(rows * H * (p + 1) * D * 2 * 2 + rows * H * D * 2 * 2 for p in positions)   # K,V prefix + q + out
     achieved = bytes_total / (ms * 1e-3) / 1e9
     return {"bound": "hbm", "kernel": "attn_decode_tma_kernel", "achieved": round(achieved, 1), "peak": peak_gbs,
-            "unit": "GB/s", "frac": round(achieved / peak_gbs, 4), "traffic": None, "peak_source": src,
+            "unit": "GB/s", "frac": round(achieved / peak_gbs, 4), "traffic": traffic, "peak_source": src,
+            "traffic_note": "ncu dram__bytes_read+write of one launch at cache position 287 (= mean position of the timed mix)",
             "launches_timed": len(positions), "avg_launch_us": round(ms * 1e3 / len(positions), 2),
             "algorithmic_bytes_per_launch_avg": bytes_total // len(positions)}
 
