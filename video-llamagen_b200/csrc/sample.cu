@@ -5,9 +5,9 @@
 // torch.multinomial can force.  One CTA owns one sample row; the V mixed logits live in shared memory
 // from the first read to the final pick, so HBM traffic is one read of the two logit rows.
 //
-//  * top-k threshold: the k-th largest value, found by a 4-pass 8-bit radix select over order-preserving
-//    keys (warp-aggregated shared-memory histograms); entries strictly below it are dropped, ties at the
-//    threshold all survive -- `logits < topk(...)[..., -1]` semantics.
+//  * top-k threshold: the k-th largest value, found by a 32-step bitwise selection over order-preserving keys held
+//    in registers (one block-wide count per bit); entries strictly below it are dropped, ties at the threshold all
+//    survive -- `logits < topk(...)[..., -1]` semantics.
 //  * top-p: in-shared-memory bitonic sort of (value desc, index asc) keys, block prefix sum of the sorted
 //    softmax, keep entry i iff i == 0 or cumsum[i-1] <= top_p (the reference's shift-right-by-one rule).
 //  * pick: argmax(probs) (greedy) or argmax(probs / Exp(1)) -- the single-draw form of torch.multinomial --
@@ -18,7 +18,6 @@
 namespace vlg {
 
 constexpr int kSampThreads = 1024;
-constexpr int kSampWarps = kSampThreads / 32;
 
 __device__ __forceinline__ uint32_t order_key(float f) {  // ascending uint order == ascending float order
   uint32_t u = __float_as_uint(f);
@@ -70,8 +69,7 @@ __global__ void __launch_bounds__(kSampThreads, 1) cfg_sample_kernel(SampleArgs 
   unsigned long long* keys = reinterpret_cast<unsigned long long*>(smraw + (((size_t)a.V * 4 + 15) & ~size_t(15)));  // [Vp2] top-p only
   __shared__ float s_redf[32];
   __shared__ int s_redi[32];
-  __shared__ unsigned s_hist[256];
-  __shared__ unsigned s_sel[2];
+  __shared__ unsigned s_cnt[3];
   __shared__ unsigned long long s_cut;
 
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -106,45 +104,37 @@ __global__ void __launch_bounds__(kSampThreads, 1) cfg_sample_kernel(SampleArgs 
   const float mx = red.max(tmax);   // row maximum; top-k / top-p never remove it
   __syncthreads();
 
-  // ---- 2. top-k threshold by radix select (k-th largest), then drop strictly-smaller entries
+  // ---- 2. top-k threshold = k-th largest key, built bit by bit from the MSB: keep bit b iff at least k keys are >= the
+  // candidate.  32 block-wide counts; the keys stay in registers (V <= 16 K), each count is 16 compares + one REDUX +
+  // one shared atomic per warp + one barrier.
   if (a.p.top_k > 0 && a.p.top_k < V) {
-    unsigned prefix = 0, pmask = 0;
-    unsigned k = (unsigned)a.p.top_k;
-    for (int shift = 24; shift >= 0; shift -= 8) {
-      if (tid < 256) s_hist[tid] = 0;
-      __syncthreads();
-      for (int i0 = 0; i0 < V; i0 += kSampThreads) {
-        int i = i0 + tid;
-        unsigned key = i < V ? order_key(val[i]) : 0u;
-        bool act = i < V && (key & pmask) == prefix;
-        unsigned digit = (key >> shift) & 0xffu;
-        // warp-aggregate equal digits so hot bins cost one shared atomic per warp
-        unsigned peers = __match_any_sync(0xffffffffu, act ? digit : 0xffffffffu);
-        if (act && lane == (__ffs(peers) - 1)) atomicAdd(&s_hist[digit], __popc(peers));
+    constexpr int kPer = 16;
+    const bool in_regs = V <= kSampThreads * kPer;
+    uint32_t keys[kPer];
+#pragma unroll
+    for (int j = 0; j < kPer; ++j) {
+      const int i = tid + j * kSampThreads;
+      keys[j] = (in_regs && i < V) ? order_key(val[i]) : 0u;
+    }
+    if (tid < 3) s_cnt[tid] = 0;
+    __syncthreads();
+    const unsigned k = (unsigned)a.p.top_k;
+    unsigned prefix = 0;
+    for (int bit = 31; bit >= 0; --bit) {
+      const unsigned cand = prefix | (1u << bit);
+      unsigned cnt = 0;
+      if (in_regs) {
+#pragma unroll
+        for (int j = 0; j < kPer; ++j) cnt += keys[j] >= cand ? 1u : 0u;
+      } else {
+        for (int i = tid; i < V; i += kSampThreads) cnt += order_key(val[i]) >= cand ? 1u : 0u;
       }
+      cnt = __reduce_add_sync(0xffffffffu, cnt);
+      unsigned* slot = &s_cnt[bit % 3];
+      if (lane == 0 && cnt) atomicAdd(slot, cnt);
       __syncthreads();
-      if (warp == 0) {  // scan bins from the top: find the digit where the running count reaches k
-        unsigned cnt[8], tot = 0;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) { cnt[j] = s_hist[255 - (lane * 8 + j)]; tot += cnt[j]; }
-        unsigned incl = tot;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { unsigned t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
-        unsigned before = incl - tot;
-        if (before < k && k <= incl) {
-          unsigned run = before;
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            if (run < k && k <= run + cnt[j]) { s_sel[0] = 255 - (lane * 8 + j); s_sel[1] = k - run; }
-            run += cnt[j];
-          }
-        }
-      }
-      __syncthreads();
-      prefix |= s_sel[0] << shift;
-      pmask |= 0xffu << shift;
-      k = s_sel[1];
-      __syncthreads();
+      if (*slot >= k) prefix = cand;
+      if (tid == 0) s_cnt[(bit + 1) % 3] = 0;       // recycled two iterations from now (a barrier lies in between)
     }
     const unsigned kth = prefix;
     for (int i = tid; i < V; i += kSampThreads)
@@ -216,33 +206,53 @@ __global__ void __launch_bounds__(kSampThreads, 1) cfg_sample_kernel(SampleArgs 
   if (a.filtered_out)
     for (int i = tid; i < V; i += kSampThreads) a.filtered_out[(size_t)b * V + i] = val[i];
 
-  // ---- 4. softmax
-  float lsum = 0.f;
-  for (int i = tid; i < V; i += kSampThreads) lsum += expf(val[i] - mx);
-  const float denom = red.sum(lsum);
+  // ---- 4. softmax denominator (only when probabilities are part of the result)
+  const bool draw = a.p.sample_logits != 0;
+  const bool exact = a.probs_out != nullptr || a.noise != nullptr || !draw;
+  float denom = 1.f;
+  if (a.probs_out) {
+    float lsum = 0.f;
+    for (int i = tid; i < V; i += kSampThreads) lsum += expf(val[i] - mx);
+    denom = red.sum(lsum);
+  }
 
   // ---- 5. pick
-  const bool draw = a.p.sample_logits != 0;
   const uint2 pkey = make_uint2((uint32_t)a.p.seed, (uint32_t)(a.p.seed >> 32));
   const uint64_t off = a.p.offset + (uint64_t)step;
   float best = -INFINITY;
   int besti = 0x7fffffff;
-  for (int i4 = tid * 4; i4 < V; i4 += kSampThreads * 4) {
-    uint4 rnd4 = make_uint4(0, 0, 0, 0);
-    if (draw && !a.noise) rnd4 = philox4x32_10(make_uint4((uint32_t)(i4 >> 2), (uint32_t)b, (uint32_t)off, (uint32_t)(off >> 32)), pkey);
-    const uint32_t rb[4] = {rnd4.x, rnd4.y, rnd4.z, rnd4.w};
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      int i = i4 + j;
-      if (i >= V) break;
-      float p = __fdiv_rn(expf(val[i] - mx), denom);
+  if (exact) {
+    // API path: argmax(probs) or argmax(probs / noise) with IEEE divisions, as torch evaluates it
+    for (int i = tid; i < V; i += kSampThreads) {
+      const float p = __fdiv_rn(expf(val[i] - mx), denom);
       if (a.probs_out) a.probs_out[(size_t)b * V + i] = p;
       float score = p;
       if (draw) {
-        float e = a.noise ? a.noise[(size_t)b * V + i] : exp1_from_bits(rb[j]);
+        float e = a.noise ? a.noise[(size_t)b * V + i] : 1.f;
+        if (!a.noise) {
+          const uint4 r4 = philox4x32_10(make_uint4((uint32_t)(i >> 2), (uint32_t)b, (uint32_t)off, (uint32_t)(off >> 32)), pkey);
+          const uint32_t rb[4] = {r4.x, r4.y, r4.z, r4.w};
+          e = exp1_from_bits(rb[i & 3]);
+        }
         score = __fdiv_rn(p, e);
       }
-      if (score > best) { best = score; besti = i; }
+      if (score > best || (score == best && i < besti)) { best = score; besti = i; }
+    }
+  } else {
+    // decode-loop path: one multinomial draw = argmax_i p_i / E_i, E_i ~ Exp(1) from Philox.  The softmax denominator
+    // is a common factor and the winner is decided in the log domain: (x_i - max) - log(E_i).
+    for (int i4 = tid * 4; i4 < V; i4 += kSampThreads * 4) {
+      const uint4 r4 = philox4x32_10(make_uint4((uint32_t)(i4 >> 2), (uint32_t)b, (uint32_t)off, (uint32_t)(off >> 32)), pkey);
+      const uint32_t rb[4] = {r4.x, r4.y, r4.z, r4.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int i = i4 + j;
+        if (i >= V) break;
+        const float x = val[i];
+        if (x == -INFINITY) continue;                                  // filtered out
+        const float score = (x - mx) - __logf(exp1_from_bits(rb[j]));
+        if (score > best) { best = score; besti = i; }
+      }
     }
   }
 #pragma unroll
