@@ -28,8 +28,8 @@ size_t align_up(size_t v, size_t a = 1024) { return (v + a - 1) / a * a; }
 int round8(int n) { return (n + 7) / 8 * 8; }
 
 struct Layout {
-  size_t k_cache, v_cache, h, xn, q, attn, ffn, logits, attn_scratch, state, norm_flags, mask, seq, labels, cond_rows,
-      prefix_emb, mlp_tmp, total;
+  size_t k_cache, v_cache, h, xn, q, attn, ffn, logits, attn_scratch, state, norm_flags, lt_bar, lt_part, mask, seq, labels,
+      cond_rows, prefix_emb, mlp_tmp, total;
 };
 
 Layout make_layout(const vlg_geometry& g, int max_rows, int max_seq) {
@@ -50,6 +50,8 @@ Layout make_layout(const vlg_geometry& g, int max_rows, int max_seq) {
   L.attn_scratch = take(attn_scratch_bytes(max_rows, g.n_head, D, S));
   L.state = take(sizeof(StepState));
   L.norm_flags = take((size_t)(2 * g.n_layer + 1) * sizeof(unsigned));   // fused-RMSNorm arrival counters, one per norm
+  L.lt_bar = take(2 * sizeof(unsigned));                                   // layer-tail grid-barrier counters
+  L.lt_part = take(g.dtype == VLG_BF16 ? layer_tail_scratch_bytes(max_rows, g.dim, g.hidden_dim) : 0);   // split-K partials
   L.mask = take((size_t)max_rows * g.cls_token_num);
   L.seq = take((size_t)max_rows * S * sizeof(int32_t));
   L.labels = take((size_t)max_rows * sizeof(int64_t));
@@ -132,6 +134,50 @@ int run_trunk(vlg_ctx* c, const int* pos_ptr, int pos_imm, int max_pos, bool fus
   void* attn = c->at<void>(c->L.attn);
   void* ffn = c->at<void>(c->L.ffn);
   unsigned* flags = c->at<unsigned>(c->L.norm_flags);
+  if (g.dtype == VLG_BF16 && layer_tail_supported(R, d, hid)) {
+    // Persistent layer-tail kernel: [norm + wqkv] in front of layer 0, then per layer attention + one launch that runs
+    // wo .. w2 of that layer and the norm + wqkv of the next one (the final norm after the last layer).
+    auto rope_params = [&](int l) {
+      EpiParams P{};
+      P.q_out = q; P.k_cache = c->kc(l); P.v_cache = c->vc(l);
+      P.rope = c->w.rope_table; P.pos_ptr = pos_ptr; P.pos_imm = pos_imm;
+      P.S_max = c->S_max; P.H = g.n_head; P.D = c->D; P.dim = d;
+      return P;
+    };
+    LtLaunch t{};
+    t.rows = R; t.dim = d; t.hidden = hid;
+    t.attn = attn; t.h = h; t.xn = xn; t.ffn = ffn;
+    t.eps = g.norm_eps;
+    t.part = c->at<float>(c->L.lt_part);
+    t.part_bytes = layer_tail_scratch_bytes(c->max_rows, d, hid);
+    t.bar = c->at<unsigned>(c->L.lt_bar);
+    int rc;
+    LtLaunch f = t;
+    f.norm2_w = c->layers[0].attention_norm; f.wqkv = c->layers[0].wqkv; f.rope = rope_params(0);
+    if ((rc = launch_layer_tail(f, st))) return rc;
+    for (int l = 0; l < g.n_layer; ++l) {
+      const vlg_layer_weights& lw = c->layers[l];
+      AttnArgs a{};
+      a.q = q; a.k_cache = c->kc(l); a.v_cache = c->vc(l); a.out = attn;
+      a.rows = R; a.H = g.n_head; a.D = c->D; a.S_max = c->S_max;
+      a.pos_ptr = pos_ptr; a.pos_imm = pos_imm; a.max_pos = max_pos;
+      a.prefix_mask = c->has_mask ? c->at<uint8_t>(c->L.mask) : nullptr;
+      a.T_prefix = c->has_mask ? g.cls_token_num : 0;
+      a.scratch = c->at<float>(c->L.attn_scratch);
+      a.scratch_bytes = attn_scratch_bytes(c->max_rows, g.n_head, c->D, c->S_max);
+      rc = !c->force_generic_attn ? launch_attn_tma(g.dtype, a, st) : launch_attn_generic(g.dtype, a, st);
+      if (rc) return rc;
+      LtLaunch m = t;
+      m.wo = lw.wo; m.w13 = lw.w13; m.w2 = lw.w2; m.norm1_w = lw.ffn_norm;
+      if (l + 1 < g.n_layer) {
+        m.norm2_w = c->layers[l + 1].attention_norm; m.wqkv = c->layers[l + 1].wqkv; m.rope = rope_params(l + 1);
+      } else {
+        m.norm2_w = c->w.norm;
+      }
+      if ((rc = launch_layer_tail(m, st))) return rc;
+    }
+    return VLG_OK;   // xn holds the final-normed hidden state
+  }
   const bool fuse = g.dtype == VLG_BF16 && !c->no_fused_norm;
   if (fuse) VLG_CUDA(cudaMemsetAsync(flags, 0, (size_t)(2 * g.n_layer + 1) * sizeof(unsigned), st));
   auto with_norm = [&](EpiParams& P, const void* weight, int idx) {
@@ -177,7 +223,7 @@ int run_head(vlg_ctx* c, float* logits, bool fused_final_norm, cudaStream_t st) 
   EpiParams P{};
   P.out = logits;
   P.ld_out = c->g.vocab_size;
-  if (fused_final_norm && c->g.dtype == VLG_BF16 && !c->no_fused_norm) {
+  if (fused_final_norm && c->g.dtype == VLG_BF16 && !c->no_fused_norm && !layer_tail_supported(c->rows, c->g.dim, c->g.hidden_dim)) {
     P.norm_src = c->at<void>(c->L.h); P.norm_weight = c->w.norm; P.norm_dst = c->at<void>(c->L.xn);
     P.norm_flag = c->at<unsigned>(c->L.norm_flags) + 2 * c->g.n_layer; P.norm_eps = c->g.norm_eps;
   }
@@ -268,6 +314,7 @@ extern "C" int vlg_ctx_create(const vlg_geometry* g, const vlg_weights* w, int m
   // the reference allocates zeroed caches (gpt.py:174-175); do it once so no stale NaN bit patterns exist
   VLG_CUDA(cudaMemset(c->ws + L.k_cache, 0, L.h - L.k_cache));
   VLG_CUDA(cudaMemset(c->state(), 0, sizeof(StepState)));
+  VLG_CUDA(cudaMemset(c->ws + L.lt_bar, 0, 2 * sizeof(unsigned)));
   VLG_CUDA(cudaDeviceSynchronize());
   *out = c;
   return VLG_OK;

@@ -34,6 +34,28 @@ size_t attn_scratch_bytes(int rows, int H, int D, int S_max);
 // bf16 only: persistent, TMA-fed streaming kernel (attn_tma.cu)
 int launch_attn_tma(int dtype, const AttnArgs& a, cudaStream_t st);
 
+// bf16, rows <= 128: everything between two attentions as one persistent kernel (layer_tail.cu).
+//   wo != null  : attn -> wo + residual -> RMSNorm(norm1_w) -> w13 -> SwiGLU -> w2 + residual, then RMSNorm(norm2_w) -> xn
+//   wo == null  : RMSNorm(norm2_w) of h -> xn only (the launch in front of layer 0)
+//   wqkv != null: xn -> wqkv -> RoPE + q / KV-cache write described by `rope`
+struct LtLaunch {
+  int rows, dim, hidden;
+  const void* attn;     // [rows, dim]
+  void* h;              // [rows, dim] residual stream, in place
+  void* xn;             // [rows, dim]
+  void* ffn;            // [rows, hidden]
+  const void *wo, *w13, *w2, *wqkv;
+  const void *norm1_w, *norm2_w;
+  float eps;
+  EpiParams rope;
+  float* part;          // split-K scratch, layer_tail_scratch_bytes()
+  size_t part_bytes;
+  unsigned* bar;        // 2 counters, zero
+};
+bool layer_tail_supported(int rows, int dim, int hidden);
+size_t layer_tail_scratch_bytes(int max_rows, int dim, int hidden);
+int launch_layer_tail(const LtLaunch& a, cudaStream_t st);
+
 // Fused CFG mix + temperature + top-k/top-p + softmax + pick.
 struct SampleArgs {
   const float* logits;  // [rows, V]

@@ -1,0 +1,532 @@
+// Everything between two attentions of the bf16 decode step as ONE persistent kernel:
+//
+//   wo(attn) + residual -> RMSNorm -> w1|w3 -> SwiGLU -> w2 + residual -> RMSNorm -> wqkv(next layer) -> RoPE + KV append
+//   (gpt.py:255-259 TransformerBlock, :143-148 RMSNorm, :151-167 FeedForward, :207-227 Attention up to the cache write)
+//
+// Why: at R <= 128 rows these GEMMs move 2-11 MB of weights each -- ~1 us of HBM time -- and as separate launches each of
+// them paid a kernel boundary, a cold TMA round trip and, worst, the whole [R x K] activation slab through every SM's
+// ~64 B/clk L2 port (profiles/README.md).  Here one CTA per SM stays resident and the step is a sequence of phases
+// separated by grid barriers (one L2 atomic + one polled load, all CTAs co-resident by construction):
+//
+//   * GEMM phases are split-K: a unit = (BN-wide column tile, K slice), at most one unit per CTA, chosen on the host so
+//     that (nearly) every SM owns one and ingests only its [128 x K/S] activation slice + [BN x K/S] weight slice through
+//     TMA (128B swizzle) into a 6-stage ring; one elected thread issues tcgen05.mma (M=128, N=BN, K=16) into a TMEM
+//     accumulator; four warps read it back (tcgen05.ld) and store the fp32 PARTIAL tile to an L2-resident scratch
+//     with 256-bit stores.  The weight tiles of the NEXT GEMM phase are requested as soon as the ring has room, i.e.
+//     while this phase's epilogue, the barrier and the row phase in between run: weights never wait on HBM latency.
+//   * Row phases reduce the S partials in a fixed order (deterministic) and apply the reference's elementwise tail with
+//     its exact rounding points (epilogue.cuh): residual add + RMSNorm (one row per CTA), SwiGLU, RoPE + cache append.
+//
+// Only the tensor-core tile is re-shaped; no arithmetic of the reference is re-associated except the fp32 K-sum order.
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace vlg {
+
+constexpr int kLtThreads = 384;            // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-9: TMEM readers (two per lane quadrant); all: row phases
+constexpr int kLtStages = 6;
+constexpr int kLtABytes = 128 * 64 * 2;    // activation tile: 128 rows x 64 k
+constexpr int kLtStageBytes = 2 * kLtABytes;   // + weight tile of up to 128 rows x 64 k
+constexpr int kLtTmemCols = 128;
+constexpr int kLtSmemBytes = kLtStages * kLtStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+
+struct LtGemm {
+  int N, K;        // out features, in features
+  int BN;          // column tile (64 or 128)
+  int S;           // K splits
+  int n_tiles;     // N / BN
+  int kb_per;      // 64-wide k-blocks per split (the last split may own fewer)
+};
+
+struct LtParams {
+  int rows, dim, hidden;
+  int has_front;   // wo .. w2 phases present (false for the launch in front of layer 0)
+  int has_qkv;     // wqkv + RoPE phases present (false after the last layer)
+  LtGemm g_wo, g_w13, g_w2, g_qkv;
+  float* part;               // split-K partials [S][rows][N] fp32, reused by every GEMM phase
+  __nv_bfloat16* h;          // residual stream [rows, dim], updated in place
+  __nv_bfloat16* xn;         // normed hidden   [rows, dim]   (A operand of w13 / wqkv / the head)
+  const __nv_bfloat16* norm1_w;   // ffn_norm of this layer
+  const __nv_bfloat16* norm2_w;   // attention_norm of the next layer, or the final norm
+  float eps;
+  EpiParams ffn;             // SwiGLU destination (out, ld_out)
+  EpiParams rope;            // RoPE + cache append parameters
+  unsigned* bar;             // [0] grid-barrier arrivals, [1] exit arrivals; both zero between launches
+  int dbg;
+};
+
+// phase timestamps (globaltimer ns) of every CTA of the last full (front + qkv) launch, VLG_LT_DEBUG=1: instrumentation
+// for tools/lt_phases.py.  Slots 0-15: thread 0 (producer / barrier view); 16-31: first TMEM-reader thread (accumulator view).
+__device__ unsigned long long g_lt_ts[160 * 32];
+#define LT_TS_AT(i)                                                                                   \
+  do {                                                                                                \
+    if (P.dbg && P.has_front && P.has_qkv && blockIdx.x < 160) {                                      \
+      unsigned long long t_;                                                                          \
+      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_));                                           \
+      g_lt_ts[blockIdx.x * 32 + (i)] = t_;                                                            \
+    }                                                                                                 \
+  } while (0)
+#define LT_TS(i) do { if (threadIdx.x == 0) LT_TS_AT(i); } while (0)
+
+struct LtUnit { int valid, n0, split, kb0, nkb; };
+
+__device__ __forceinline__ LtUnit lt_unit(const LtGemm& G, int cta) {
+  LtUnit u;
+  u.valid = cta < G.n_tiles * G.S;
+  const int tile = cta % G.n_tiles;      // neighbouring CTAs share the activation slice and differ in the weight tile
+  u.split = cta / G.n_tiles;
+  u.n0 = tile * G.BN;
+  u.kb0 = u.split * G.kb_per;
+  const int nkb = G.K / 64;
+  u.nkb = min(G.kb_per, nkb - u.kb0);
+  return u;
+}
+
+__device__ __forceinline__ void stg256(float* p, const float* v) {
+  asm volatile("st.global.cg.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]),
+               "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
+}
+// 16 bf16 (32 bytes = one full L2 sector) in one store
+__device__ __forceinline__ void stg256_bf16x16(__nv_bfloat16* p, const float* o) {
+  asm volatile("st.global.cg.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(pack_bf16(o[0], o[1])), "r"(pack_bf16(o[2], o[3])),
+               "r"(pack_bf16(o[4], o[5])), "r"(pack_bf16(o[6], o[7])), "r"(pack_bf16(o[8], o[9])), "r"(pack_bf16(o[10], o[11])),
+               "r"(pack_bf16(o[12], o[13])), "r"(pack_bf16(o[14], o[15])) : "memory");
+}
+// L2-coherent loads: everything a row phase reads was written by other SMs earlier in this same kernel
+__device__ __forceinline__ void ldg256(const float* p, float* v) {
+  asm volatile("ld.global.cg.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]) : "l"(p));
+}
+__device__ __forceinline__ uint4 ldg128_cg(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+
+// All CTAs of the grid are co-resident (grid <= SM count, one CTA per SM): arrive with a release add, poll with acquire.
+__device__ __forceinline__ void lt_grid_barrier(unsigned* ctr, unsigned& target) {
+  target += gridDim.x;
+  tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    // release: cumulative over the CTA's stores ordered before it by the bar.sync above (tools/micro/bar_bench.cu: the
+    // extra fences of the cooperative-groups recipe cost 0.25 us per barrier and add nothing to this pattern)
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
+    unsigned seen, spins = 0;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(ctr) : "memory");
+      if (++spins > (1u << 25)) { printf("vlg: layer-tail grid barrier timeout (block %d, %u < %u)\n", blockIdx.x, seen, target); __trap(); }
+    } while (seen < target);
+  }
+  __syncthreads();
+  tc_fence_after();
+}
+
+struct LtSmem {
+  uint64_t full[kLtStages], empty[kLtStages];
+  uint64_t acc_ready;
+  uint32_t tmem_slot;
+  float red[kLtThreads / 32];
+};
+
+// ---------------------------------------------------------------------------------------------------- GEMM phase
+// g: k-blocks this CTA has pushed through the ring so far (producer and MMA issuer walk the same sequence);
+// acc_uses: GEMM phases in which this CTA owned a unit (parity of acc_ready).
+__device__ __forceinline__ void lt_prefetch_b(const LtGemm& G, const TensorMap* tmB, uint8_t* ring, LtSmem& sm, uint32_t g) {
+  const LtUnit v = lt_unit(G, blockIdx.x);
+  if (!v.valid) return;
+  const int pre = v.nkb < kLtStages ? v.nkb : kLtStages;
+  const uint32_t tx = kLtABytes + G.BN * 128;
+  for (int kb = 0; kb < pre; ++kb) {
+    const uint32_t s = (g + kb) % kLtStages, it = (g + kb) / kLtStages;
+    mbar_wait(&sm.empty[s], (it & 1) ^ 1);
+    mbar_expect_tx(&sm.full[s], tx);
+    tma_load_2d_hint(ring + s * kLtStageBytes + kLtABytes, tmB, &sm.full[s], (v.kb0 + kb) * 64, v.n0, kEvictFirst);
+  }
+}
+
+// MODE: -1 = store the fp32 partial tile (split-K, reduced by the following row phase); EPI_SWIGLU / EPI_QKV_ROPE = the unit
+// owns all of K and applies the elementwise tail straight from TMEM (lane == row).
+template <int MODE>
+__device__ __forceinline__ void lt_gemm_phase(const LtGemm& G, const TensorMap* tmA, const TensorMap* tmB,
+                                              const LtGemm* Gnext, const TensorMap* tmBnext, const LtParams& P,
+                                              const EpiParams& E, uint8_t* ring, LtSmem& sm, uint32_t tmem_acc, uint32_t& g, uint32_t& acc_uses,
+                                              int ts_slot) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const LtUnit u = lt_unit(G, blockIdx.x);
+  const uint32_t nkb = u.valid ? (uint32_t)u.nkb : 0u;
+  if (warp == 0) {
+    if (elect_one()) {
+      asm volatile("fence.proxy.async;" ::: "memory");     // other SMs' generic-proxy stores of A -> this SM's TMA reads
+      if (u.valid) {
+        const int pre = u.nkb < kLtStages ? u.nkb : kLtStages;      // their weight tiles + expect_tx were issued a phase ago
+        for (int kb = 0; kb < pre; ++kb) {
+          const uint32_t s = (g + kb) % kLtStages;
+          tma_load_2d_hint(ring + s * kLtStageBytes, tmA, &sm.full[s], (u.kb0 + kb) * 64, 0, kEvictLast);
+        }
+        const uint32_t tx = kLtABytes + G.BN * 128;
+        for (int kb = pre; kb < u.nkb; ++kb) {
+          const uint32_t s = (g + kb) % kLtStages, it = (g + kb) / kLtStages;
+          mbar_wait(&sm.empty[s], (it & 1) ^ 1);
+          mbar_expect_tx(&sm.full[s], tx);
+          uint8_t* a = ring + s * kLtStageBytes;
+          tma_load_2d_hint(a, tmA, &sm.full[s], (u.kb0 + kb) * 64, 0, kEvictLast);
+          tma_load_2d_hint(a + kLtABytes, tmB, &sm.full[s], (u.kb0 + kb) * 64, u.n0, kEvictFirst);
+        }
+      }
+      if (Gnext != nullptr) lt_prefetch_b(*Gnext, tmBnext, ring, sm, g + nkb);
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (u.valid && elect_one()) {
+      const uint32_t idesc = umma_idesc_bf16(128, G.BN);
+      for (int kb = 0; kb < u.nkb; ++kb) {
+        const uint32_t s = (g + kb) % kLtStages, it = (g + kb) / kLtStages;
+        mbar_wait(&sm.full[s], it & 1);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(ring + s * kLtStageBytes);
+        const uint64_t adesc = umma_desc_sw128(a_addr), bdesc = umma_desc_sw128(a_addr + kLtABytes);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_bf16(tmem_acc, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+        umma_commit(&sm.empty[s]);
+      }
+      umma_commit(&sm.acc_ready);
+    }
+    __syncwarp();
+  } else if (warp < 10) {
+    if (u.valid) {
+      // TMEM lane quadrant = warp % 4 (hardware rule); the two warps of a quadrant split the columns.  Every store below
+      // covers whole 32-byte sectors: partial-sector writes cost the L2 several times their size.
+      const int quad = warp & 3, half = (warp - 2) >> 2, r = quad * 32 + lane;
+      const uint32_t lane_base = tmem_acc + (static_cast<uint32_t>(quad * 32) << 16);
+      mbar_wait(&sm.acc_ready, acc_uses & 1);
+      tc_fence_after();
+      if (threadIdx.x == 64) LT_TS_AT(ts_slot);
+      if constexpr (MODE < 0) {
+        float* dst = P.part + ((size_t)u.split * P.rows + r) * G.N + u.n0;
+        for (int c = half * 16; c < G.BN; c += 32) {
+          float v[16];
+          tmem_ld16(lane_base + c, v);
+          if (r < P.rows) {
+            stg256(dst + c, v);
+            stg256(dst + c + 8, v + 8);
+          }
+        }
+      } else if constexpr (MODE == EPI_SWIGLU) {      // gpt.py:167 -- w1/w3 rows interleaved: columns (2j, 2j+1) = (w1 x, w3 x)_j
+        for (int c = half * 32; c < G.BN; c += 64) {
+          float v[32];
+          tmem_ld16(lane_base + c, v);
+          tmem_ld16(lane_base + c + 16, v + 16);
+          if (r < P.rows) {
+            float o[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float a = rnd<__nv_bfloat16>(v[2 * i]), b = rnd<__nv_bfloat16>(v[2 * i + 1]);
+              o[i] = __fmul_rn(rnd<__nv_bfloat16>(silu_f(a)), b);
+            }
+            stg256_bf16x16(static_cast<__nv_bfloat16*>(E.out) + (size_t)r * E.ld_out + ((u.n0 + c) >> 1), o);
+          }
+        }
+      } else {                                         // EPI_QKV_ROPE on 16 columns (a quarter head): gpt.py:215-227, 423-433, 177-185
+        const int pos = E.pos_ptr ? *E.pos_ptr : E.pos_imm;
+        for (int c = half * 16; c < G.BN; c += 32) {
+          float v[16];
+          tmem_ld16(lane_base + c, v);
+          if (r < P.rows) {
+            const int n = u.n0 + c, sec = n / E.dim, cc = n - sec * E.dim, head = cc / E.D, dd = cc - head * E.D;
+            float o[16];
+            if (sec < 2) {
+              const float2* tab = reinterpret_cast<const float2*>(E.rope) + (size_t)pos * (E.D >> 1) + (dd >> 1);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float2 cs = tab[i];
+                const float x0 = rnd<__nv_bfloat16>(v[2 * i]), x1 = rnd<__nv_bfloat16>(v[2 * i + 1]);
+                o[2 * i] = __fsub_rn(__fmul_rn(x0, cs.x), __fmul_rn(x1, cs.y));
+                o[2 * i + 1] = __fadd_rn(__fmul_rn(x1, cs.x), __fmul_rn(x0, cs.y));
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) o[i] = v[i];
+            }
+            __nv_bfloat16* dst;
+            if (sec == 0) dst = static_cast<__nv_bfloat16*>(E.q_out) + (size_t)r * E.dim + cc;
+            else dst = static_cast<__nv_bfloat16*>(sec == 1 ? E.k_cache : E.v_cache) + (((size_t)r * E.H + head) * E.S_max + pos) * E.D + dd;
+            stg256_bf16x16(dst, o);
+          }
+        }
+      }
+      if (threadIdx.x == 64) LT_TS_AT(ts_slot + 1);
+    }
+  }
+  g += nkb;
+  acc_uses += u.valid ? 1u : 0u;
+}
+
+// ---------------------------------------------------------------------------------------------------- row phases
+// sum of the S partials of 8 consecutive columns, fixed order
+__device__ __forceinline__ void lt_reduce8(const float* part, int S, size_t split_stride, size_t off, float* acc) {
+  constexpr int kChunk = 8;          // loads in flight per thread before the first dependent add
+  float t[kChunk][8];
+#pragma unroll
+  for (int j = 0; j < kChunk; ++j)
+    if (j < S) ldg256(part + (size_t)j * split_stride + off, t[j]);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = t[0][i];
+#pragma unroll
+  for (int j = 1; j < kChunk; ++j)
+    if (j < S) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] = __fadd_rn(acc[i], t[j][i]);
+    }
+  for (int s0 = kChunk; s0 < S; s0 += kChunk) {
+#pragma unroll
+    for (int j = 0; j < kChunk; ++j)
+      if (s0 + j < S) ldg256(part + (size_t)(s0 + j) * split_stride + off, t[j]);
+#pragma unroll
+    for (int j = 0; j < kChunk; ++j)
+      if (s0 + j < S) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = __fadd_rn(acc[i], t[j][i]);
+      }
+  }
+}
+
+// h <- T(h + T(sum of partials))  (when G != null), then xn <- T(T(h * rsqrt(mean(h^2) + eps)) * w): one row per CTA
+__device__ __forceinline__ void lt_norm_phase(const LtGemm* G, const __nv_bfloat16* w, const LtParams& P, LtSmem& sm) {
+  const int nvec = P.dim / 8, t = threadIdx.x;
+  const bool active = t < nvec;
+  float g8[8];
+  if (active) load8<__nv_bfloat16>(w + t * 8, g8);
+  for (int r = blockIdx.x; r < P.rows; r += gridDim.x) {
+    float hn[8];
+    float ss = 0.f;
+    if (active) {
+      __nv_bfloat16* hp = P.h + (size_t)r * P.dim + t * 8;
+      const uint4 hu = ldg128_cg(hp);
+      hn[0] = bf16lo(hu.x); hn[1] = bf16hi(hu.x); hn[2] = bf16lo(hu.y); hn[3] = bf16hi(hu.y);
+      hn[4] = bf16lo(hu.z); hn[5] = bf16hi(hu.z); hn[6] = bf16lo(hu.w); hn[7] = bf16hi(hu.w);
+      if (G != nullptr) {
+        float acc[8];
+        lt_reduce8(P.part, G->S, (size_t)P.rows * G->N, (size_t)r * G->N + t * 8, acc);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) hn[i] = rnd<__nv_bfloat16>(__fadd_rn(hn[i], rnd<__nv_bfloat16>(acc[i])));
+        store8<__nv_bfloat16>(hp, hn);
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) ss = __fadd_rn(ss, __fmul_rn(hn[i], hn[i]));
+    }
+    ss = warp_sum(ss);
+    __syncthreads();                                   // previous row's readers of sm.red are done
+    if ((t & 31) == 0) sm.red[t >> 5] = ss;
+    __syncthreads();
+    float tot = 0.f;
+#pragma unroll
+    for (int i = 0; i < kLtThreads / 32; ++i) tot += sm.red[i];
+    const float rs = rsqrtf(__fdiv_rn(tot, (float)P.dim) + P.eps);
+    if (active) {
+      float o[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = __fmul_rn(rnd<__nv_bfloat16>(__fmul_rn(hn[i], rs)), g8[i]);
+      store8<__nv_bfloat16>(P.xn + (size_t)r * P.dim + t * 8, o);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------- the kernel
+__global__ void __launch_bounds__(kLtThreads, 1)
+layer_tail_kernel(const __grid_constant__ TensorMap tmAttn, const __grid_constant__ TensorMap tmXn,
+                  const __grid_constant__ TensorMap tmFfn, const __grid_constant__ TensorMap tmWo,
+                  const __grid_constant__ TensorMap tmW13, const __grid_constant__ TensorMap tmW2,
+                  const __grid_constant__ TensorMap tmWqkv, const LtParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  LtSmem& sm = *reinterpret_cast<LtSmem*>(ring + kLtStages * kLtStageBytes);
+  const int warp = threadIdx.x >> 5;
+
+  if (threadIdx.x == 0) {
+    if (P.has_front) { tma_prefetch_desc(&tmAttn); tma_prefetch_desc(&tmFfn); tma_prefetch_desc(&tmWo); tma_prefetch_desc(&tmW13); tma_prefetch_desc(&tmW2); }
+    tma_prefetch_desc(&tmXn);
+    if (P.has_qkv) tma_prefetch_desc(&tmWqkv);
+    for (int s = 0; s < kLtStages; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], 1); }
+    mbar_init(&sm.acc_ready, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<kLtTmemCols>(&sm.tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_acc = sm.tmem_slot;
+
+  LT_TS(0);
+  pdl_launch_dependents();
+  uint32_t g = 0, acc_uses = 0;
+  unsigned bar_target = 0;
+  // the first GEMM's weight tiles do not depend on the previous kernel: request them before waiting for it
+  if (warp == 0) {
+    if (elect_one()) {
+      if (P.has_front) lt_prefetch_b(P.g_wo, &tmWo, ring, sm, 0);
+      else if (P.has_qkv) lt_prefetch_b(P.g_qkv, &tmWqkv, ring, sm, 0);
+    }
+    __syncwarp();
+  }
+  pdl_wait();
+  LT_TS(1);
+
+  if (P.has_front) {
+    lt_gemm_phase<-1>(P.g_wo, &tmAttn, &tmWo, &P.g_w13, &tmW13, P, P.ffn, ring, sm, tmem_acc, g, acc_uses, 16);
+    LT_TS(2);
+    lt_grid_barrier(P.bar, bar_target);
+    LT_TS(3);
+    lt_norm_phase(&P.g_wo, P.norm1_w, P, sm);
+    LT_TS(4);
+    lt_grid_barrier(P.bar, bar_target);
+    LT_TS(5);
+    lt_gemm_phase<EPI_SWIGLU>(P.g_w13, &tmXn, &tmW13, &P.g_w2, &tmW2, P, P.ffn, ring, sm, tmem_acc, g, acc_uses, 18);
+    LT_TS(6);
+    lt_grid_barrier(P.bar, bar_target);
+    LT_TS(7);
+    lt_gemm_phase<-1>(P.g_w2, &tmFfn, &tmW2, P.has_qkv ? &P.g_qkv : nullptr, &tmWqkv, P, P.ffn, ring, sm, tmem_acc, g, acc_uses, 20);
+    LT_TS(8);
+    lt_grid_barrier(P.bar, bar_target);
+    LT_TS(9);
+    lt_norm_phase(&P.g_w2, P.norm2_w, P, sm);
+    LT_TS(10);
+  } else {
+    lt_norm_phase(nullptr, P.norm2_w, P, sm);
+  }
+  if (P.has_qkv) {
+    lt_grid_barrier(P.bar, bar_target);
+    LT_TS(11);
+    lt_gemm_phase<EPI_QKV_ROPE>(P.g_qkv, &tmXn, &tmWqkv, nullptr, nullptr, P, P.rope, ring, sm, tmem_acc, g, acc_uses, 22);
+    LT_TS(12);
+  }
+
+  // leave the counters at zero for the next launch: the last CTA out has seen everyone past the final barrier
+  tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned old = atomicAdd(P.bar + 1, 1u);
+    if (old == gridDim.x - 1) {
+      P.bar[0] = 0;
+      P.bar[1] = 0;
+      __threadfence();
+    }
+  }
+  if (warp == 1) tmem_dealloc<kLtTmemCols>(tmem_acc);
+}
+
+// ---------------------------------------------------------------------------------------------------- host
+// Tile shape and split count per GEMM: bytes a CTA pulls through its L2 port (activation + weight slices), pushes out
+// (partial tile) and the row phase pulls back, with at most one unit per CTA.
+// Split-K units write fp32 partials: the L2 write path sustains only ~4.3 TB/s over the chip (tools/micro/bar_bench.cu), so
+// a stored byte is costed 4x a loaded one.  Units that own all of K (split == false) need room for one tile per CTA.
+static bool lt_pick(int N, int K, int sms, bool split, LtGemm* out) {
+  if (K % 64 != 0 || N % 64 != 0) return false;
+  const int nkb = K / 64;
+  double best = 1e30;
+  bool found = false;
+  const int bns[3] = {32, 64, 128};
+  for (int bn : bns) {
+    if (N % bn) continue;
+    const int tiles = N / bn;
+    if (tiles > sms) continue;
+    int s0 = split ? sms / tiles : 1;
+    if (s0 > nkb) s0 = nkb;
+    const int kb_per = (nkb + s0 - 1) / s0;
+    const int S = (nkb + kb_per - 1) / kb_per;
+    // costed at the full 128-row tile so that the choice (and the scratch size) does not depend on the batch
+    double cost = (double)kb_per * (128 + bn) * 128.0;
+    if (split) cost += 4.0 * 128.0 * bn * 4.0 + (double)S * 128 * N * 4.0 / sms;
+    if (cost < best) {
+      best = cost;
+      found = true;
+      out->N = N; out->K = K; out->BN = bn; out->S = S; out->n_tiles = tiles; out->kb_per = kb_per;
+    }
+  }
+  return found;
+}
+
+bool layer_tail_supported(int rows, int dim, int hidden) {
+  static const bool off = [] { const char* e = getenv("VLG_LT"); return e && e[0] == '0'; }();
+  if (off) return false;
+  if (rows <= 0 || rows > 128 || dim % 64 != 0 || hidden % 64 != 0 || dim / 8 > kLtThreads) return false;
+  const int sms = num_sms();
+  LtGemm t;
+  return lt_pick(dim, dim, sms, true, &t) && lt_pick(2 * hidden, dim, sms, false, &t) && lt_pick(dim, hidden, sms, true, &t) &&
+         lt_pick(3 * dim, dim, sms, false, &t);
+}
+
+size_t layer_tail_scratch_bytes(int max_rows, int dim, int hidden) {
+  const int rows = max_rows < 128 ? max_rows : 128;
+  const int sms = num_sms();
+  size_t worst = 0;
+  const int shapes[2][2] = {{dim, dim}, {dim, hidden}};   // wo and w2 are the split-K GEMMs
+  for (auto& sh : shapes) {
+    LtGemm t;
+    if (!lt_pick(sh[0], sh[1], sms, true, &t)) continue;
+    const size_t b = (size_t)t.S * rows * t.N * sizeof(float);
+    if (b > worst) worst = b;
+  }
+  return worst + 1024;
+}
+
+int launch_layer_tail(const LtLaunch& a, cudaStream_t st) {
+  VLG_REQUIRE(layer_tail_supported(a.rows, a.dim, a.hidden), "layer_tail: unsupported shape rows=%d dim=%d hidden=%d", a.rows, a.dim, a.hidden);
+  VLG_REQUIRE(a.wo || a.wqkv, "layer_tail: nothing to do");
+  const int sms = num_sms();
+  LtParams P{};
+  P.rows = a.rows; P.dim = a.dim; P.hidden = a.hidden;
+  P.has_front = a.wo != nullptr;
+  P.has_qkv = a.wqkv != nullptr;
+  lt_pick(a.dim, a.dim, sms, true, &P.g_wo);
+  lt_pick(2 * a.hidden, a.dim, sms, false, &P.g_w13);
+  lt_pick(a.dim, a.hidden, sms, true, &P.g_w2);
+  lt_pick(3 * a.dim, a.dim, sms, false, &P.g_qkv);
+  const LtGemm* gs[2] = {&P.g_wo, &P.g_w2};
+  for (const LtGemm* g : gs)
+    VLG_REQUIRE((size_t)g->S * a.rows * g->N * sizeof(float) <= a.part_bytes, "layer_tail: scratch too small (%zu bytes)", a.part_bytes);
+  P.part = a.part;
+  P.h = static_cast<__nv_bfloat16*>(a.h);
+  P.xn = static_cast<__nv_bfloat16*>(a.xn);
+  P.norm1_w = static_cast<const __nv_bfloat16*>(a.norm1_w);
+  P.norm2_w = static_cast<const __nv_bfloat16*>(a.norm2_w);
+  P.eps = a.eps;
+  P.ffn.out = a.ffn; P.ffn.ld_out = a.hidden;
+  P.rope = a.rope;
+  P.bar = a.bar;
+  static const int dbg = [] { const char* e = getenv("VLG_LT_DEBUG"); return e ? atoi(e) : 0; }();
+  P.dbg = dbg;
+
+  TensorMap tmAttn{}, tmXn{}, tmFfn{}, tmWo{}, tmW13{}, tmW2{}, tmWqkv{};
+  int rc;
+  if ((rc = make_tmap_bf16_2d(&tmXn, a.xn, (uint64_t)a.rows, (uint64_t)a.dim, (uint64_t)a.dim * 2, 128, 64, true))) return rc;
+  if (P.has_front) {
+    if ((rc = make_tmap_bf16_2d(&tmAttn, a.attn, (uint64_t)a.rows, (uint64_t)a.dim, (uint64_t)a.dim * 2, 128, 64, true))) return rc;
+    if ((rc = make_tmap_bf16_2d(&tmFfn, a.ffn, (uint64_t)a.rows, (uint64_t)a.hidden, (uint64_t)a.hidden * 2, 128, 64, true))) return rc;
+    if ((rc = make_tmap_bf16_2d(&tmWo, a.wo, (uint64_t)a.dim, (uint64_t)a.dim, (uint64_t)a.dim * 2, P.g_wo.BN, 64, true))) return rc;
+    if ((rc = make_tmap_bf16_2d(&tmW13, a.w13, (uint64_t)2 * a.hidden, (uint64_t)a.dim, (uint64_t)a.dim * 2, P.g_w13.BN, 64, true))) return rc;
+    if ((rc = make_tmap_bf16_2d(&tmW2, a.w2, (uint64_t)a.dim, (uint64_t)a.hidden, (uint64_t)a.hidden * 2, P.g_w2.BN, 64, true))) return rc;
+  }
+  if (P.has_qkv)
+    if ((rc = make_tmap_bf16_2d(&tmWqkv, a.wqkv, (uint64_t)3 * a.dim, (uint64_t)a.dim, (uint64_t)a.dim * 2, P.g_qkv.BN, 64, true))) return rc;
+
+  static bool attr_set = false;
+  if (!attr_set) {
+    VLG_CUDA(cudaFuncSetAttribute(layer_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kLtSmemBytes));
+    attr_set = true;
+  }
+  VLG_CUDA(launch_kernel(layer_tail_kernel, dim3(sms), dim3(kLtThreads), (size_t)kLtSmemBytes, st, tmAttn, tmXn, tmFfn, tmWo,
+                         tmW13, tmW2, tmWqkv, P));
+  VLG_LAUNCH_CHECK();
+  return VLG_OK;
+}
+
+}  // namespace vlg
+
+// instrumentation: phase timestamps (ns), [160 CTAs][32 slots], of the last full layer-tail launch run with VLG_LT_DEBUG=1
+extern "C" int vlg_debug_lt_timestamps(unsigned long long* out_host) {
+  VLG_CUDA(cudaMemcpyFromSymbol(out_host, vlg::g_lt_ts, sizeof(unsigned long long) * 160 * 32));
+  return VLG_OK;
+}
