@@ -3,7 +3,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libvlg.so")
+LIB_PATH = os.environ.get("VLG_LIB_PATH") or os.path.join(os.path.dirname(_HERE), "lib", "libvlg.so")   # override: A/B builds
 
 VLG_F32, VLG_BF16 = 0, 1
 VLG_C2I, VLG_T2I, VLG_T2V = 0, 1, 2
