@@ -15,19 +15,18 @@ torch.nn.init.normal_(m.output.weight, std=0.02)
 m = m.to("cuda", torch.bfloat16)
 cond = torch.randint(0, 1000, (64,)).cuda()
 n_new = int(sys.argv[1]) if len(sys.argv) > 1 else 288
-names = {0: "attn start", 1: "attn done", 13: "bar", 2: "wo issued", 3: "bar", 4: "norm1", 5: "bar", 6: "w13 issued", 7: "bar",
-         8: "w2 issued", 9: "bar", 10: "norm2", 11: "bar", 12: "qkv issued", 16: "wo acc", 17: "wo epi", 18: "w13 acc",
-         19: "w13 epi", 20: "w2 acc", 21: "w2 epi", 22: "qkv acc", 23: "qkv epi"}
-order = [0, 1, 13, 2, 16, 17, 3, 4, 5, 6, 18, 19, 7, 8, 20, 21, 9, 10, 11, 12, 22, 23]
+names = {0: "start", 1: "pdl_wait", 2: "wo issued", 3: "bar", 4: "norm1", 5: "bar", 6: "w13 issued", 7: "bar", 8: "w2 issued",
+         9: "bar", 10: "norm2", 11: "bar", 12: "qkv issued", 16: "wo acc", 17: "wo epi", 18: "w13 acc", 19: "w13 epi",
+         20: "w2 acc", 21: "w2 epi", 22: "qkv acc", 23: "qkv epi"}
 for rep in range(2):
     generate(m, cond, n_new, cfg_scale=4.0, temperature=1.0, top_k=2000, top_p=1.0, sample_logits=True, seed=rep)
     torch.cuda.synchronize()
 ts = (C.c_ulonglong * (160 * 32))()
 L.check(lib.vlg_debug_lt_timestamps(ts))
 t = np.array(ts, dtype=np.int64).reshape(160, 32)[:148].astype(np.float64)
-t0 = t[:, 0][t[:, 0] > 0].min()          # first CTA into the (middle layer's) attention phase
-print(f"new_tokens {n_new}; middle layer; us relative to the first CTA entering attention; min / median / max over CTAs")
-for k in order:
+t0 = t[:, 1].min()          # first CTA past pdl_wait
+print(f"new_tokens {n_new}; times in us relative to the first CTA leaving pdl_wait; min / median / max over CTAs that have the stamp")
+for k in sorted(names):
     col = t[:, k]
     col = col[col > 0] - t0
     if len(col):

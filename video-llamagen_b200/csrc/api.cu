@@ -28,7 +28,7 @@ size_t align_up(size_t v, size_t a = 1024) { return (v + a - 1) / a * a; }
 int round8(int n) { return (n + 7) / 8 * 8; }
 
 struct Layout {
-  size_t k_cache, v_cache, h, xn, q, attn, ffn, logits, attn_scratch, state, norm_flags, lt_bar, lt_part, dl_desc, mask, seq, labels,
+  size_t k_cache, v_cache, h, xn, q, attn, ffn, logits, attn_scratch, state, norm_flags, lt_bar, lt_part, mask, seq, labels,
       cond_rows, prefix_emb, mlp_tmp, total;
 };
 
@@ -52,7 +52,6 @@ Layout make_layout(const vlg_geometry& g, int max_rows, int max_seq) {
   L.norm_flags = take((size_t)(2 * g.n_layer + 1) * sizeof(unsigned));   // fused-RMSNorm arrival counters, one per norm
   L.lt_bar = take(2 * sizeof(unsigned));                                   // layer-tail grid-barrier counters
   L.lt_part = take(g.dtype == VLG_BF16 ? layer_tail_scratch_bytes(max_rows, g.dim, g.hidden_dim) : 0);   // split-K partials
-  L.dl_desc = take(g.dtype == VLG_BF16 ? decode_layers_desc_bytes(g.n_layer) : 0);   // per-layer weight tensor maps (whole-trunk kernel)
   L.mask = take((size_t)max_rows * g.cls_token_num);
   L.seq = take((size_t)max_rows * S * sizeof(int32_t));
   L.labels = take((size_t)max_rows * sizeof(int64_t));
@@ -78,7 +77,6 @@ struct vlg_ctx {
   int rows = 0;
   bool has_mask = false;
   bool force_generic_attn = false;   // VLG_ATTN=generic: A/B the two attention kernels
-  bool dl_ready = false;             // per-layer descriptors of the whole-trunk kernel are encoded
   bool no_fused_norm = true;         // VLG_FUSED_NORM=1 enables the fused RMSNorm prologue of the GEMMs (A/B)
   // graph capture is illegal on the legacy default stream (torch's default): such callers are forked onto this one
   cudaStream_t own_stream = nullptr;
@@ -136,24 +134,6 @@ int run_trunk(vlg_ctx* c, const int* pos_ptr, int pos_imm, int max_pos, bool fus
   void* attn = c->at<void>(c->L.attn);
   void* ffn = c->at<void>(c->L.ffn);
   unsigned* flags = c->at<unsigned>(c->L.norm_flags);
-  if (g.dtype == VLG_BF16 && c->dl_ready && !c->force_generic_attn && decode_layers_supported(R, d, hid, g.n_head)) {
-    // One persistent kernel for all layers of this position (attention included).
-    DlLaunch t{};
-    t.rows = R; t.dim = d; t.hidden = hid; t.n_layer = g.n_layer; t.H = g.n_head; t.S_max = c->S_max; t.max_rows = c->max_rows;
-    t.attn = attn; t.h = h; t.xn = xn; t.ffn = ffn;
-    t.final_norm_w = c->w.norm;
-    t.eps = g.norm_eps;
-    t.rope.q_out = q; t.rope.k_cache = c->kc(0); t.rope.v_cache = c->vc(0);
-    t.rope.rope = c->w.rope_table; t.rope.pos_ptr = pos_ptr; t.rope.pos_imm = pos_imm;
-    t.rope.S_max = c->S_max; t.rope.H = g.n_head; t.rope.D = c->D; t.rope.dim = d;
-    t.mask = c->has_mask ? c->at<uint8_t>(c->L.mask) : nullptr;
-    t.T_prefix = c->has_mask ? g.cls_token_num : 0;
-    t.part = c->at<float>(c->L.lt_part);
-    t.part_bytes = layer_tail_scratch_bytes(c->max_rows, d, hid);
-    t.bar = c->at<unsigned>(c->L.lt_bar);
-    t.desc_dev = c->at<void>(c->L.dl_desc);
-    return launch_decode_layers(t, st);   // xn holds the final-normed hidden state
-  }
   if (g.dtype == VLG_BF16 && layer_tail_supported(R, d, hid)) {
     // Persistent layer-tail kernel: [norm + wqkv] in front of layer 0, then per layer attention + one launch that runs
     // wo .. w2 of that layer and the norm + wqkv of the next one (the final norm after the last layer).
@@ -335,16 +315,6 @@ extern "C" int vlg_ctx_create(const vlg_geometry* g, const vlg_weights* w, int m
   VLG_CUDA(cudaMemset(c->ws + L.k_cache, 0, L.h - L.k_cache));
   VLG_CUDA(cudaMemset(c->state(), 0, sizeof(StepState)));
   VLG_CUDA(cudaMemset(c->ws + L.lt_bar, 0, 2 * sizeof(unsigned)));
-  if (g->dtype == VLG_BF16 && layer_tail_supported(1, g->dim, g->hidden_dim)) {
-    std::vector<DlLayerHost> hl((size_t)g->n_layer);
-    for (int l = 0; l < g->n_layer; ++l) {
-      const vlg_layer_weights& lw = c->layers[l];
-      hl[l] = DlLayerHost{lw.wo, lw.w13, lw.w2, lw.wqkv, lw.attention_norm, lw.ffn_norm};
-    }
-    int rc = decode_layers_encode(c->ws + L.dl_desc, hl.data(), g->n_layer, g->dim, g->hidden_dim);
-    if (rc) { delete c; return rc; }
-    c->dl_ready = true;
-  }
   VLG_CUDA(cudaDeviceSynchronize());
   *out = c;
   return VLG_OK;

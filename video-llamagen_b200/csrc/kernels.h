@@ -56,27 +56,6 @@ bool layer_tail_supported(int rows, int dim, int hidden);
 size_t layer_tail_scratch_bytes(int max_rows, int dim, int hidden);
 int launch_layer_tail(const LtLaunch& a, cudaStream_t st);
 
-// bf16, rows <= 128, rows * H >= 2 * SMs: ALL transformer blocks of one position as one persistent kernel (layer_tail.cu).
-struct DlLayerHost { const void *wo, *w13, *w2, *wqkv, *attn_norm, *ffn_norm; };
-struct DlLaunch {
-  int rows, dim, hidden, n_layer, H, S_max, max_rows;
-  const void* attn;     // [rows, dim] attention output buffer
-  void *h, *xn, *ffn;
-  const void* final_norm_w;
-  float eps;
-  EpiParams rope;       // q_out, k_cache / v_cache of layer 0 (layers are max_rows*H*S_max*D apart), table, position
-  const uint8_t* mask;  // prefix mask [rows, T_prefix] or null
-  int T_prefix;
-  float* part;
-  size_t part_bytes;
-  unsigned* bar;
-  const void* desc_dev; // decode_layers_encode() output
-};
-bool decode_layers_supported(int rows, int dim, int hidden, int n_head);
-size_t decode_layers_desc_bytes(int n_layer);
-int decode_layers_encode(void* desc_dev, const DlLayerHost* layers, int n_layer, int dim, int hidden);
-int launch_decode_layers(const DlLaunch& a, cudaStream_t st);
-
 // Fused CFG mix + temperature + top-k/top-p + softmax + pick.
 struct SampleArgs {
   const float* logits;  // [rows, V]

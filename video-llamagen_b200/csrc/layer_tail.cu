@@ -19,30 +19,22 @@
 //
 // Only the tensor-core tile is re-shaped; no arithmetic of the reference is re-associated except the fp32 K-sum order.
 #include <stdlib.h>
-#include <vector>
 
-#include "attn_tma.cuh"
 #include "common.cuh"
 #include "kernels.h"
 
 namespace vlg {
 
-#ifndef LT_THREADS
-#define LT_THREADS 384
-#endif
-constexpr int kLtThreads = LT_THREADS;     // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner (attention: merger), warps 2-9: TMEM readers,
-                                           // two per lane quadrant (attention: consumers); all warps: row phases
+constexpr int kLtThreads = 384;            // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-9: TMEM readers (two per lane quadrant); all: row phases
 constexpr int kLtStages = 6;
 constexpr int kLtABytes = 128 * 64 * 2;    // activation tile: 128 rows x 64 k
-constexpr int kLtBBytes = 64 * 64 * 2;     // weight tile: up to 64 rows x 64 k (BN <= 64: shared memory left to L1 matters
-                                           // more than wider tiles -- the attention phase's working set lives there)
-constexpr int kLtStageBytes = kLtABytes + kLtBBytes;
-constexpr int kLtTmemCols = 64;
+constexpr int kLtStageBytes = 2 * kLtABytes;   // + weight tile of up to 128 rows x 64 k
+constexpr int kLtTmemCols = 128;
 constexpr int kLtSmemBytes = kLtStages * kLtStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 
 struct LtGemm {
   int N, K;        // out features, in features
-  int BN;          // column tile (32 or 64)
+  int BN;          // column tile (64 or 128)
   int S;           // K splits
   int n_tiles;     // N / BN
   int kb_per;      // 64-wide k-blocks per split (the last split may own fewer)
@@ -70,13 +62,13 @@ struct LtParams {
 __device__ unsigned long long g_lt_ts[160 * 32];
 #define LT_TS_AT(i)                                                                                   \
   do {                                                                                                \
-    if (P.dbg && (i) >= 0 && blockIdx.x < 160) {                                                      \
+    if (P.dbg && P.has_front && P.has_qkv && blockIdx.x < 160) {                                      \
       unsigned long long t_;                                                                          \
       asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_));                                           \
       g_lt_ts[blockIdx.x * 32 + (i)] = t_;                                                            \
     }                                                                                                 \
   } while (0)
-#define LT_TS(i) do { if (threadIdx.x == 0) LT_TS_AT(ts_on ? (i) : -1); } while (0)
+#define LT_TS(i) do { if (threadIdx.x == 0) LT_TS_AT(i); } while (0)
 
 struct LtUnit { int valid, n0, split, kb0, nkb; };
 
@@ -103,15 +95,9 @@ __device__ __forceinline__ void stg256_bf16x16(__nv_bfloat16* p, const float* o)
                "r"(pack_bf16(o[12], o[13])), "r"(pack_bf16(o[14], o[15])) : "memory");
 }
 // L2-coherent loads: everything a row phase reads was written by other SMs earlier in this same kernel
-// WIDE: one 256-bit load; otherwise two 128-bit loads (the 256-bit asm form crashes cicc 12.9 inside a __noinline__ function)
-template <bool WIDE> __device__ __forceinline__ void ldg256(const float* p, float* v) {
-  if constexpr (WIDE) {
-    asm volatile("ld.global.cg.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]) : "l"(p));
-  } else {
-    const float4 a = __ldcg(reinterpret_cast<const float4*>(p)), b = __ldcg(reinterpret_cast<const float4*>(p) + 1);
-    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-  }
+__device__ __forceinline__ void ldg256(const float* p, float* v) {
+  asm volatile("ld.global.cg.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]) : "l"(p));
 }
 __device__ __forceinline__ uint4 ldg128_cg(const void* p) {
   uint4 r;
@@ -163,18 +149,11 @@ __device__ __forceinline__ void lt_prefetch_b(const LtGemm& G, const TensorMap* 
 
 // MODE: -1 = store the fp32 partial tile (split-K, reduced by the following row phase); EPI_SWIGLU / EPI_QKV_ROPE = the unit
 // owns all of K and applies the elementwise tail straight from TMEM (lane == row).
-// The GEMM phase is always inlined (a __noinline__ build of it produced wrong results on B200 with nvcc 12.9 -- not
-// understood, kept switchable for A/B builds).  The whole-trunk kernel calls the attention and norm phases through
-// __noinline__ wrappers: with every phase inlined its loop-invariant state stayed live across the attention tile loop and
-// spilled inside it.
-#ifndef LT_GEMM_ATTR
-#define LT_GEMM_ATTR __forceinline__
-#endif
 template <int MODE>
-__device__ LT_GEMM_ATTR void lt_gemm_phase(const LtGemm& G, const TensorMap* tmA, const TensorMap* tmB,
+__device__ __forceinline__ void lt_gemm_phase(const LtGemm& G, const TensorMap* tmA, const TensorMap* tmB,
                                               const LtGemm* Gnext, const TensorMap* tmBnext, const LtParams& P,
                                               const EpiParams& E, uint8_t* ring, LtSmem& sm, uint32_t tmem_acc, uint32_t& g, uint32_t& acc_uses,
-                                              int ts_slot, size_t kv_off = 0) {
+                                              int ts_slot) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const LtUnit u = lt_unit(G, blockIdx.x);
   const uint32_t nkb = u.valid ? (uint32_t)u.nkb : 0u;
@@ -273,12 +252,12 @@ __device__ LT_GEMM_ATTR void lt_gemm_phase(const LtGemm& G, const TensorMap* tmA
             }
             __nv_bfloat16* dst;
             if (sec == 0) dst = static_cast<__nv_bfloat16*>(E.q_out) + (size_t)r * E.dim + cc;
-            else dst = static_cast<__nv_bfloat16*>(sec == 1 ? E.k_cache : E.v_cache) + kv_off + (((size_t)r * E.H + head) * E.S_max + pos) * E.D + dd;
+            else dst = static_cast<__nv_bfloat16*>(sec == 1 ? E.k_cache : E.v_cache) + (((size_t)r * E.H + head) * E.S_max + pos) * E.D + dd;
             stg256_bf16x16(dst, o);
           }
         }
       }
-      if (threadIdx.x == 64) LT_TS_AT(ts_slot < 0 ? -1 : ts_slot + 1);
+      if (threadIdx.x == 64) LT_TS_AT(ts_slot + 1);
     }
   }
   g += nkb;
@@ -287,35 +266,35 @@ __device__ LT_GEMM_ATTR void lt_gemm_phase(const LtGemm& G, const TensorMap* tmA
 
 // ---------------------------------------------------------------------------------------------------- row phases
 // sum of the S partials of 8 consecutive columns, fixed order
-template <bool WIDE>
 __device__ __forceinline__ void lt_reduce8(const float* part, int S, size_t split_stride, size_t off, float* acc) {
-  // up to eight loads in flight before the first dependent add; the order of the adds is fixed (s = 0, 1, 2, ...)
-  const float* p = part + off;
-  for (int s0 = 0; s0 < S; s0 += 8) {
-    float t[8][8];
+  constexpr int kChunk = 8;          // loads in flight per thread before the first dependent add
+  float t[kChunk][8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j)
-      if (s0 + j < S) ldg256<WIDE>(p + (size_t)(s0 + j) * split_stride, t[j]);
+  for (int j = 0; j < kChunk; ++j)
+    if (j < S) ldg256(part + (size_t)j * split_stride + off, t[j]);
 #pragma unroll
-    for (int j = 0; j < 8; ++j)
+  for (int i = 0; i < 8; ++i) acc[i] = t[0][i];
+#pragma unroll
+  for (int j = 1; j < kChunk; ++j)
+    if (j < S) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] = __fadd_rn(acc[i], t[j][i]);
+    }
+  for (int s0 = kChunk; s0 < S; s0 += kChunk) {
+#pragma unroll
+    for (int j = 0; j < kChunk; ++j)
+      if (s0 + j < S) ldg256(part + (size_t)(s0 + j) * split_stride + off, t[j]);
+#pragma unroll
+    for (int j = 0; j < kChunk; ++j)
       if (s0 + j < S) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) acc[i] = (s0 + j == 0) ? t[j][i] : __fadd_rn(acc[i], t[j][i]);
+        for (int i = 0; i < 8; ++i) acc[i] = __fadd_rn(acc[i], t[j][i]);
       }
   }
 }
 
-// h <- T(h + T(sum of partials))  (when S > 0), then xn <- T(T(h * rsqrt(mean(h^2) + eps)) * w): one row per CTA
-// S = 0: plain RMSNorm of h.
-struct LtNormArgs {          // by value: a reference to the kernel's parameter block would force a local-memory copy of it
-  const float* part;
-  __nv_bfloat16* h;
-  __nv_bfloat16* xn;
-  int rows, dim;
-  float eps;
-};
-template <bool WIDE>
-__device__ __forceinline__ void lt_norm_phase(int S, int N, const __nv_bfloat16* w, const LtNormArgs P, float* red) {
+// h <- T(h + T(sum of partials))  (when G != null), then xn <- T(T(h * rsqrt(mean(h^2) + eps)) * w): one row per CTA
+__device__ __forceinline__ void lt_norm_phase(const LtGemm* G, const __nv_bfloat16* w, const LtParams& P, LtSmem& sm) {
   const int nvec = P.dim / 8, t = threadIdx.x;
   const bool active = t < nvec;
   float g8[8];
@@ -328,9 +307,9 @@ __device__ __forceinline__ void lt_norm_phase(int S, int N, const __nv_bfloat16*
       const uint4 hu = ldg128_cg(hp);
       hn[0] = bf16lo(hu.x); hn[1] = bf16hi(hu.x); hn[2] = bf16lo(hu.y); hn[3] = bf16hi(hu.y);
       hn[4] = bf16lo(hu.z); hn[5] = bf16hi(hu.z); hn[6] = bf16lo(hu.w); hn[7] = bf16hi(hu.w);
-      if (S > 0) {
+      if (G != nullptr) {
         float acc[8];
-        lt_reduce8<WIDE>(P.part, S, (size_t)P.rows * N, (size_t)r * N + t * 8, acc);
+        lt_reduce8(P.part, G->S, (size_t)P.rows * G->N, (size_t)r * G->N + t * 8, acc);
 #pragma unroll
         for (int i = 0; i < 8; ++i) hn[i] = rnd<__nv_bfloat16>(__fadd_rn(hn[i], rnd<__nv_bfloat16>(acc[i])));
         store8<__nv_bfloat16>(hp, hn);
@@ -339,12 +318,12 @@ __device__ __forceinline__ void lt_norm_phase(int S, int N, const __nv_bfloat16*
       for (int i = 0; i < 8; ++i) ss = __fadd_rn(ss, __fmul_rn(hn[i], hn[i]));
     }
     ss = warp_sum(ss);
-    __syncthreads();                                   // previous row's readers of red[] are done
-    if ((t & 31) == 0) red[t >> 5] = ss;
+    __syncthreads();                                   // previous row's readers of sm.red are done
+    if ((t & 31) == 0) sm.red[t >> 5] = ss;
     __syncthreads();
     float tot = 0.f;
 #pragma unroll
-    for (int i = 0; i < kLtThreads / 32; ++i) tot += red[i];
+    for (int i = 0; i < kLtThreads / 32; ++i) tot += sm.red[i];
     const float rs = rsqrtf(__fdiv_rn(tot, (float)P.dim) + P.eps);
     if (active) {
       float o[8];
@@ -360,7 +339,7 @@ __global__ void __launch_bounds__(kLtThreads, 1)
 layer_tail_kernel(const __grid_constant__ TensorMap tmAttn, const __grid_constant__ TensorMap tmXn,
                   const __grid_constant__ TensorMap tmFfn, const __grid_constant__ TensorMap tmWo,
                   const __grid_constant__ TensorMap tmW13, const __grid_constant__ TensorMap tmW2,
-                  const __grid_constant__ TensorMap tmWqkv, const __grid_constant__ LtParams P) {
+                  const __grid_constant__ TensorMap tmWqkv, const LtParams P) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   LtSmem& sm = *reinterpret_cast<LtSmem*>(ring + kLtStages * kLtStageBytes);
@@ -379,8 +358,6 @@ layer_tail_kernel(const __grid_constant__ TensorMap tmAttn, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_acc = sm.tmem_slot;
-  const bool ts_on = P.has_front && P.has_qkv;
-  const LtNormArgs NA{P.part, P.h, P.xn, P.rows, P.dim, P.eps};
 
   LT_TS(0);
   pdl_launch_dependents();
@@ -398,200 +375,35 @@ layer_tail_kernel(const __grid_constant__ TensorMap tmAttn, const __grid_constan
   LT_TS(1);
 
   if (P.has_front) {
-    lt_gemm_phase<-1>(P.g_wo, &tmAttn, &tmWo, &P.g_w13, &tmW13, P, P.ffn, ring, sm, tmem_acc, g, acc_uses, ts_on ? 16 : -1);
+    lt_gemm_phase<-1>(P.g_wo, &tmAttn, &tmWo, &P.g_w13, &tmW13, P, P.ffn, ring, sm, tmem_acc, g, acc_uses, 16);
     LT_TS(2);
     lt_grid_barrier(P.bar, bar_target);
     LT_TS(3);
-    lt_norm_phase<true>(P.g_wo.S, P.g_wo.N, P.norm1_w, NA, sm.red);
+    lt_norm_phase(&P.g_wo, P.norm1_w, P, sm);
     LT_TS(4);
     lt_grid_barrier(P.bar, bar_target);
     LT_TS(5);
-    lt_gemm_phase<EPI_SWIGLU>(P.g_w13, &tmXn, &tmW13, &P.g_w2, &tmW2, P, P.ffn, ring, sm, tmem_acc, g, acc_uses, ts_on ? 18 : -1);
+    lt_gemm_phase<EPI_SWIGLU>(P.g_w13, &tmXn, &tmW13, &P.g_w2, &tmW2, P, P.ffn, ring, sm, tmem_acc, g, acc_uses, 18);
     LT_TS(6);
     lt_grid_barrier(P.bar, bar_target);
     LT_TS(7);
-    lt_gemm_phase<-1>(P.g_w2, &tmFfn, &tmW2, P.has_qkv ? &P.g_qkv : nullptr, &tmWqkv, P, P.ffn, ring, sm, tmem_acc, g, acc_uses, ts_on ? 20 : -1);
+    lt_gemm_phase<-1>(P.g_w2, &tmFfn, &tmW2, P.has_qkv ? &P.g_qkv : nullptr, &tmWqkv, P, P.ffn, ring, sm, tmem_acc, g, acc_uses, 20);
     LT_TS(8);
     lt_grid_barrier(P.bar, bar_target);
     LT_TS(9);
-    lt_norm_phase<true>(P.g_w2.S, P.g_w2.N, P.norm2_w, NA, sm.red);
+    lt_norm_phase(&P.g_w2, P.norm2_w, P, sm);
     LT_TS(10);
   } else {
-    lt_norm_phase<true>(0, 0, P.norm2_w, NA, sm.red);
+    lt_norm_phase(nullptr, P.norm2_w, P, sm);
   }
   if (P.has_qkv) {
     lt_grid_barrier(P.bar, bar_target);
     LT_TS(11);
-    lt_gemm_phase<EPI_QKV_ROPE>(P.g_qkv, &tmXn, &tmWqkv, nullptr, nullptr, P, P.rope, ring, sm, tmem_acc, g, acc_uses, ts_on ? 22 : -1);
+    lt_gemm_phase<EPI_QKV_ROPE>(P.g_qkv, &tmXn, &tmWqkv, nullptr, nullptr, P, P.rope, ring, sm, tmem_acc, g, acc_uses, 22);
     LT_TS(12);
   }
 
   // leave the counters at zero for the next launch: the last CTA out has seen everyone past the final barrier
-  tc_fence_before();
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    const unsigned old = atomicAdd(P.bar + 1, 1u);
-    if (old == gridDim.x - 1) {
-      P.bar[0] = 0;
-      P.bar[1] = 0;
-      __threadfence();
-    }
-  }
-  if (warp == 1) tmem_dealloc<kLtTmemCols>(tmem_acc);
-}
-
-
-// ==================================================================================================== whole trunk
-// All N transformer blocks of one decode position as ONE persistent kernel: the layer-tail phases above plus the
-// attention phase (attn_tma.cuh) on the same shared-memory ring, a grid barrier wherever the data flow is all-to-all.
-//   norm -> wqkv(0)+RoPE | for each layer: attention | wo | norm | w1,w3+SwiGLU | w2 | norm | wqkv(l+1)+RoPE
-// Per-layer weight tensor maps live in device memory (encoded once per context); the K/V maps cover the caches of all
-// layers, a layer is a row offset.  Used when (row, head) items alone fill the SMs (no sequence splits).
-constexpr int kDlSlots = 8;
-
-struct alignas(64) DlLayer {
-  TensorMap tmWo, tmW13, tmW2, tmWqkv;
-  const __nv_bfloat16* attn_norm_w;
-  const __nv_bfloat16* ffn_norm_w;
-};
-
-struct DlParams {
-  LtParams lt;                 // rows/dim/hidden, tile shapes, scratch, h/xn, ffn + rope params (cache pointers = layer 0)
-  int n_layer;
-  const DlLayer* layers;
-  const __nv_bfloat16* final_norm_w;
-  size_t kv_layer_elems;       // elements between the caches of consecutive layers
-  int kv_layer_rows;           // the same in tensor-map rows (positions)
-  const __nv_bfloat16* q;
-  __nv_bfloat16* attn_out;
-  int n_rh, H, S_max;
-  const int* pos_ptr;
-  int pos_imm;
-  const uint8_t* mask;
-  int T_prefix;
-  int dbg_layer;
-};
-
-struct DlSmemTail {
-  AttnSide<kDlSlots> side;
-  LtSmem lt;
-};
-constexpr int kDlSmemBytes = kLtStages * kLtStageBytes + (int)sizeof(DlSmemTail) + 1024;
-static_assert(kAttnRingBytes <= kLtStages * kLtStageBytes, "the attention ring must fit inside the GEMM ring");
-static_assert(kDlSmemBytes <= 227 * 1024, "decode_layers_kernel: shared memory budget");
-
-// __noinline__: the attention phase gets its own register allocation (inlined, the kernel's loop-invariant state stayed
-// live across the 150-register consumer loop and spilled inside it).
-__device__ __noinline__ void dl_norm_phase(int S, int N, const __nv_bfloat16* w, const LtNormArgs P, float* red) {
-  lt_norm_phase<false>(S, N, w, P, red);
-}
-
-template <bool QSMEM>
-__device__ __noinline__ void dl_attention_phase(uint8_t* ring, AttnSide<kDlSlots>& side, const TensorMap* tmK, const TensorMap* tmV,
-                                               const AttnPhaseArgs& A, int role, int cw, AttnProgress& prog) {
-  attn_tma_phase<kDlSlots, QSMEM, true>(ring, side, tmK, tmV, A, role, cw, prog);
-}
-
-template <bool QSMEM>
-__global__ void __launch_bounds__(kLtThreads, 1)
-decode_layers_kernel(const __grid_constant__ TensorMap tmAttn, const __grid_constant__ TensorMap tmXn,
-                     const __grid_constant__ TensorMap tmFfn, const __grid_constant__ TensorMap tmK,
-                     const __grid_constant__ TensorMap tmV, const __grid_constant__ DlParams D) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  DlSmemTail& tail = *reinterpret_cast<DlSmemTail*>(ring + kLtStages * kLtStageBytes);
-  LtSmem& sm = tail.lt;
-  const LtParams& P = D.lt;
-  const int warp = threadIdx.x >> 5;
-
-  if (threadIdx.x == 0) {
-    tma_prefetch_desc(&tmAttn); tma_prefetch_desc(&tmXn); tma_prefetch_desc(&tmFfn);
-    tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
-    tma_prefetch_desc(&D.layers[0].tmWqkv);
-    for (int s = 0; s < kLtStages; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], 1); }
-    mbar_init(&sm.acc_ready, 1);
-    attn_side_init(tail.side);
-    fence_mbar_init();
-  }
-  if (warp == 1) tmem_alloc<kLtTmemCols>(&sm.tmem_slot);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_acc = sm.tmem_slot;
-  const LtNormArgs NA{P.part, P.h, P.xn, P.rows, P.dim, P.eps};
-
-  pdl_launch_dependents();
-  uint32_t g = 0, acc_uses = 0;
-  unsigned bar_target = 0;
-  AttnProgress prog{0u, 0u};
-  const int attn_role = warp == 0 ? ATTN_PRODUCER : (warp == 1 ? ATTN_MERGER : (warp < 2 + kCW ? ATTN_CONSUMER : ATTN_IDLE));
-  bool ts_on = false;
-  if (warp == 0) {                       // weights do not depend on the previous kernel
-    if (elect_one()) lt_prefetch_b(P.g_qkv, &D.layers[0].tmWqkv, ring, sm, 0);
-    __syncwarp();
-  }
-  pdl_wait();
-  const int pos = D.pos_ptr ? *D.pos_ptr : D.pos_imm;
-
-  dl_norm_phase(0, 0, D.layers[0].attn_norm_w, NA, sm.red);
-  lt_grid_barrier(P.bar, bar_target);
-  lt_gemm_phase<EPI_QKV_ROPE>(P.g_qkv, &tmXn, &D.layers[0].tmWqkv, nullptr, nullptr, P, P.rope, ring, sm, tmem_acc, g, acc_uses, -1);
-
-  for (int l = 0; l < D.n_layer; ++l) {
-    const DlLayer& Ly = D.layers[l];
-    const bool last = l + 1 == D.n_layer;
-    ts_on = l == D.dbg_layer;
-    if (threadIdx.x == 0) {
-      tma_prefetch_desc(&Ly.tmWo); tma_prefetch_desc(&Ly.tmW13); tma_prefetch_desc(&Ly.tmW2);
-      if (!last) tma_prefetch_desc(&D.layers[l + 1].tmWqkv);
-    }
-    lt_grid_barrier(P.bar, bar_target);          // q and the K/V rows of this position are in place
-    LT_TS(0);
-
-    // ---- attention over the cache prefix of layer l (the ring is free: the wqkv MMAs retired before the barrier)
-    AttnPhaseArgs A;
-    A.q = D.q; A.out = D.attn_out; A.part = nullptr;
-    A.n_rh = D.n_rh; A.H = D.H; A.S_max = D.S_max;
-    A.tile_row_base = l * D.kv_layer_rows;
-    A.pos = pos; A.mask = D.mask; A.T_prefix = D.T_prefix; A.n_splits = 1;
-    dl_attention_phase<QSMEM>(ring, tail.side, &tmK, &tmV, A, attn_role, warp - 2, prog);
-    LT_TS(1);
-    __syncthreads();                             // every consumer of this CTA is done with the ring
-    if (warp == 0) {
-      if (elect_one()) lt_prefetch_b(P.g_wo, &Ly.tmWo, ring, sm, g);
-      __syncwarp();
-    }
-    lt_grid_barrier(P.bar, bar_target);
-    LT_TS(13);
-
-    lt_gemm_phase<-1>(P.g_wo, &tmAttn, &Ly.tmWo, &P.g_w13, &Ly.tmW13, P, P.ffn, ring, sm, tmem_acc, g, acc_uses, ts_on ? 16 : -1);
-    LT_TS(2);
-    lt_grid_barrier(P.bar, bar_target);
-    LT_TS(3);
-    dl_norm_phase(P.g_wo.S, P.g_wo.N, Ly.ffn_norm_w, NA, sm.red);
-    LT_TS(4);
-    lt_grid_barrier(P.bar, bar_target);
-    LT_TS(5);
-    lt_gemm_phase<EPI_SWIGLU>(P.g_w13, &tmXn, &Ly.tmW13, &P.g_w2, &Ly.tmW2, P, P.ffn, ring, sm, tmem_acc, g, acc_uses, ts_on ? 18 : -1);
-    LT_TS(6);
-    lt_grid_barrier(P.bar, bar_target);
-    LT_TS(7);
-    lt_gemm_phase<-1>(P.g_w2, &tmFfn, &Ly.tmW2, last ? nullptr : &P.g_qkv, last ? nullptr : &D.layers[l + 1].tmWqkv, P, P.ffn,
-                      ring, sm, tmem_acc, g, acc_uses, ts_on ? 20 : -1);
-    LT_TS(8);
-    lt_grid_barrier(P.bar, bar_target);
-    LT_TS(9);
-    dl_norm_phase(P.g_w2.S, P.g_w2.N, last ? D.final_norm_w : D.layers[l + 1].attn_norm_w, NA, sm.red);
-    LT_TS(10);
-    if (!last) {
-      lt_grid_barrier(P.bar, bar_target);
-      LT_TS(11);
-      lt_gemm_phase<EPI_QKV_ROPE>(P.g_qkv, &tmXn, &D.layers[l + 1].tmWqkv, nullptr, nullptr, P, P.rope, ring, sm, tmem_acc, g, acc_uses,
-                                  ts_on ? 22 : -1, (size_t)(l + 1) * D.kv_layer_elems);
-      LT_TS(12);
-    }
-  }
-
   tc_fence_before();
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -615,7 +427,7 @@ static bool lt_pick(int N, int K, int sms, bool split, LtGemm* out) {
   const int nkb = K / 64;
   double best = 1e30;
   bool found = false;
-  const int bns[2] = {32, 64};
+  const int bns[3] = {32, 64, 128};
   for (int bn : bns) {
     if (N % bn) continue;
     const int tiles = N / bn;
@@ -707,97 +519,6 @@ int launch_layer_tail(const LtLaunch& a, cudaStream_t st) {
   }
   VLG_CUDA(launch_kernel(layer_tail_kernel, dim3(sms), dim3(kLtThreads), (size_t)kLtSmemBytes, st, tmAttn, tmXn, tmFfn, tmWo,
                          tmW13, tmW2, tmWqkv, P));
-  VLG_LAUNCH_CHECK();
-  return VLG_OK;
-}
-
-
-// ---------------------------------------------------------------------------------------------------- whole-trunk host side
-size_t decode_layers_desc_bytes(int n_layer) { return (size_t)n_layer * sizeof(DlLayer); }
-
-bool decode_layers_supported(int rows, int dim, int hidden, int n_head) {
-  // Opt-in (VLG_DL=1): measured 42.4k tok/s at cfg-2 against 45.0k for per-layer launches (attention kernel + layer-tail
-  // kernel) -- the two kernel boundaries it removes cost about what its two extra grid barriers and the colder
-  // instruction cache of the 96 KB kernel cost.
-  static const bool on = [] { const char* e = getenv("VLG_DL"); return e && e[0] == '1'; }();
-  if (!on || !layer_tail_supported(rows, dim, hidden)) return false;
-  return dim / n_head == 64 && rows * n_head >= 2 * num_sms();   // (row, head) items fill the SMs: no sequence splits
-}
-
-int decode_layers_encode(void* desc_dev, const DlLayerHost* layers, int n_layer, int dim, int hidden) {
-  const int sms = num_sms();
-  LtGemm g_wo, g_w13, g_w2, g_qkv;
-  VLG_REQUIRE(lt_pick(dim, dim, sms, true, &g_wo) && lt_pick(2 * hidden, dim, sms, false, &g_w13) &&
-              lt_pick(dim, hidden, sms, true, &g_w2) && lt_pick(3 * dim, dim, sms, false, &g_qkv),
-              "decode_layers: unsupported shape dim=%d hidden=%d", dim, hidden);
-  std::vector<DlLayer> host((size_t)n_layer);
-  for (int l = 0; l < n_layer; ++l) {
-    int rc;
-    memset(&host[l], 0, sizeof(DlLayer));
-    if ((rc = make_tmap_bf16_2d(&host[l].tmWo, layers[l].wo, (uint64_t)dim, (uint64_t)dim, (uint64_t)dim * 2, g_wo.BN, 64, true))) return rc;
-    if ((rc = make_tmap_bf16_2d(&host[l].tmW13, layers[l].w13, (uint64_t)2 * hidden, (uint64_t)dim, (uint64_t)dim * 2, g_w13.BN, 64, true))) return rc;
-    if ((rc = make_tmap_bf16_2d(&host[l].tmW2, layers[l].w2, (uint64_t)dim, (uint64_t)hidden, (uint64_t)hidden * 2, g_w2.BN, 64, true))) return rc;
-    if ((rc = make_tmap_bf16_2d(&host[l].tmWqkv, layers[l].wqkv, (uint64_t)3 * dim, (uint64_t)dim, (uint64_t)dim * 2, g_qkv.BN, 64, true))) return rc;
-    host[l].attn_norm_w = static_cast<const __nv_bfloat16*>(layers[l].attn_norm);
-    host[l].ffn_norm_w = static_cast<const __nv_bfloat16*>(layers[l].ffn_norm);
-  }
-  VLG_CUDA(cudaMemcpy(desc_dev, host.data(), host.size() * sizeof(DlLayer), cudaMemcpyHostToDevice));
-  return VLG_OK;
-}
-
-int launch_decode_layers(const DlLaunch& a, cudaStream_t st) {
-  VLG_REQUIRE(decode_layers_supported(a.rows, a.dim, a.hidden, a.H), "decode_layers: unsupported shape rows=%d dim=%d hidden=%d H=%d",
-              a.rows, a.dim, a.hidden, a.H);
-  const int sms = num_sms();
-  DlParams D{};
-  LtParams& P = D.lt;
-  P.rows = a.rows; P.dim = a.dim; P.hidden = a.hidden;
-  P.has_front = 1; P.has_qkv = 1;
-  lt_pick(a.dim, a.dim, sms, true, &P.g_wo);
-  lt_pick(2 * a.hidden, a.dim, sms, false, &P.g_w13);
-  lt_pick(a.dim, a.hidden, sms, true, &P.g_w2);
-  lt_pick(3 * a.dim, a.dim, sms, false, &P.g_qkv);
-  const LtGemm* gs[2] = {&P.g_wo, &P.g_w2};
-  for (const LtGemm* g : gs)
-    VLG_REQUIRE((size_t)g->S * a.rows * g->N * sizeof(float) <= a.part_bytes, "decode_layers: scratch too small (%zu bytes)", a.part_bytes);
-  P.part = a.part;
-  P.h = static_cast<__nv_bfloat16*>(a.h);
-  P.xn = static_cast<__nv_bfloat16*>(a.xn);
-  P.eps = a.eps;
-  P.ffn.out = a.ffn; P.ffn.ld_out = a.hidden;
-  P.rope = a.rope;
-  P.bar = a.bar;
-  static const int dbg = [] { const char* e = getenv("VLG_LT_DEBUG"); return e ? atoi(e) : 0; }();
-  P.dbg = dbg;
-  D.dbg_layer = a.n_layer / 2;
-  D.n_layer = a.n_layer;
-  D.layers = static_cast<const DlLayer*>(a.desc_dev);
-  D.final_norm_w = static_cast<const __nv_bfloat16*>(a.final_norm_w);
-  D.kv_layer_rows = a.max_rows * a.H * a.S_max;
-  D.kv_layer_elems = (size_t)D.kv_layer_rows * 64;
-  D.q = static_cast<const __nv_bfloat16*>(a.rope.q_out);
-  D.attn_out = static_cast<__nv_bfloat16*>(const_cast<void*>(a.attn));
-  D.n_rh = a.rows * a.H; D.H = a.H; D.S_max = a.S_max;
-  D.pos_ptr = a.rope.pos_ptr; D.pos_imm = a.rope.pos_imm;
-  D.mask = a.mask; D.T_prefix = a.mask ? a.T_prefix : 0;
-
-  const uint64_t kv_rows = (uint64_t)a.n_layer * D.kv_layer_rows;
-  VLG_REQUIRE(kv_rows < (1ull << 31), "decode_layers: cache too large for 32-bit TMA coordinates");
-  TensorMap tmAttn{}, tmXn{}, tmFfn{}, tmK{}, tmV{};
-  int rc;
-  if ((rc = make_tmap_bf16_2d(&tmXn, a.xn, (uint64_t)a.rows, (uint64_t)a.dim, (uint64_t)a.dim * 2, 128, 64, true))) return rc;
-  if ((rc = make_tmap_bf16_2d(&tmAttn, a.attn, (uint64_t)a.rows, (uint64_t)a.dim, (uint64_t)a.dim * 2, 128, 64, true))) return rc;
-  if ((rc = make_tmap_bf16_2d(&tmFfn, a.ffn, (uint64_t)a.rows, (uint64_t)a.hidden, (uint64_t)a.hidden * 2, 128, 64, true))) return rc;
-  if ((rc = make_tmap_bf16_2d(&tmK, a.rope.k_cache, kv_rows, 64, 128, kTile, 64, true))) return rc;
-  if ((rc = make_tmap_bf16_2d(&tmV, a.rope.v_cache, kv_rows, 64, 128, kTile, 64, true))) return rc;
-
-  auto kern = decode_layers_kernel<true>;   // query staged in shared memory: with it in registers the tile loop spills (measured 83 us per phase)
-  static bool attr_set = false;
-  if (!attr_set) {
-    VLG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kDlSmemBytes));
-    attr_set = true;
-  }
-  VLG_CUDA(launch_kernel(kern, dim3(sms), dim3(kLtThreads), (size_t)kDlSmemBytes, st, tmAttn, tmXn, tmFfn, tmK, tmV, D));
   VLG_LAUNCH_CHECK();
   return VLG_OK;
 }
