@@ -158,6 +158,33 @@ def test_gptl_cfg2_full_size_bf16():
     assert rms_ours <= 1.5 * rms_ref + 1e-4, (rms_ours, rms_ref)       # no noisier than the reference's own bf16 run
 
 
+@pytest.mark.parametrize("name,n_layer,B", [("GPT-B", 3, 4), ("GPT-XL", 2, 8), ("GPT-XXL", 2, 32), ("GPT-1B", 2, 64)])
+def test_layer_tail_geometries_bf16(name, n_layer, B):
+    """The persistent layer-tail kernel (split-K tile shapes, ring wrap-around, row phases) at the widths of the other
+    registry entries -- d = 768 / 1280 / 1536 / 2048, hidden 2048 / 3584 / 4096 / 5632, 8..128 cache rows -- on a few
+    layers: teacher-forced bf16 logits against the oracle on the same GPU."""
+    kw = dict(O.NAMED[name])
+    kw["n_layer"] = n_layer
+    geo = O.Geometry(block_size=64, vocab_size=1024, **kw)
+    w = O.init_weights(geo, seed=3, dtype=torch.float32, embed_std=0.3)
+    m = Transformer(ModelArgs(block_size=64, vocab_size=1024, cls_token_num=1, model_type="c2i", **kw)).eval()
+    m.load_state_dict(w, strict=True)
+    m = m.to(DEV, torch.bfloat16)
+    g = torch.Generator().manual_seed(5)
+    cond = torch.randint(0, 1000, (B,), generator=g).to(DEV)
+    toks = torch.randint(0, 1024, (B, 12), generator=g).to(DEV)
+    w16 = {k: v.to(DEV, torch.bfloat16) for k, v in w.items()}
+    ref = O.teacher_forced_logits(geo, w16, cond, toks)
+    truth = O.teacher_forced_logits(geo, {k: v.float() for k, v in w16.items()}, cond, toks)
+    rows = torch.cat([cond, torch.ones_like(cond) * 1000])
+    ours = teacher_forced(m, rows, toks, 1).float()
+    scale = max(1.0, truth.pow(2).mean().sqrt().item() / 0.55)
+    assert torch.allclose(ours, ref, rtol=BF16_RTOL, atol=BF16_ATOL * scale), ((ours - ref).abs().max(), scale)
+    rms_ours = (ours - truth).pow(2).mean().sqrt().item()
+    rms_ref = (ref - truth).pow(2).mean().sqrt().item()
+    assert rms_ours <= 1.5 * rms_ref + 1e-4, (rms_ours, rms_ref)
+
+
 def test_t2v_tiny_trunk_adapters_3d_rope(golden):
     """BASELINE cfg-4 path at fixture size: 120-token masked caption prefix, CFG row doubling, latent adapters in/out,
     3D RoPE table, continuous-latent output (gpt_video.py:403-431) -- fp32 against the reference fixture, then bf16
