@@ -179,6 +179,18 @@ typedef struct {
 int vlg_generate(vlg_ctx* ctx, const vlg_generate_params* p, const void* cond_dev, const void* uncond_dev,
                  const uint8_t* emb_masks_dev, int32_t* tokens_dev, void* stream);
 
+/* t2v (gpt_video.py trunk, SURVEY.md 8a row a17 / BASELINE cfg-4): the loop the reference's samplers call as
+ * `generate(gpt_model, c_indices, vae_t * latent_size**2, c_emb_masks, cfg_scale=...)` (sample_t2v_1f.py:199-205; the
+ * module it imports, models/generate_video.py, is missing from the fork).  The model emits a continuous latent per
+ * position -- no logits, no sampler: prefill over the T caption positions, then N-1 steps of
+ *   latent_s = cfg_mix(vae_latent_adapter2(hidden))  ->  next input = vae_latent_adapter(latent_s).
+ * cond_dev dtype [B, T, caption_dim]; uncond_dev dtype [T, caption_dim] (needed when cfg_scale > 1); emb_masks_dev
+ * uint8 [B, T] or NULL; latents_dev dtype [B, max_new_tokens, vae_embed_dim].  temperature / top_k / top_p /
+ * sample_logits / seed of the params are ignored.  bf16: vae_latent_adapter.fc1 zero-padded to 64 input columns and
+ * vae_latent_adapter2.fc2 to 16 output rows by the caller (tensor-core tile granularity). */
+int vlg_generate_t2v(vlg_ctx* ctx, const vlg_generate_params* p, const void* cond_dev, const void* uncond_dev,
+                     const uint8_t* emb_masks_dev, void* latents_dev, void* stream);
+
 /* Same with HOST buffers (pinned or pageable): copies cond in, runs, copies tokens out and synchronises
  * the stream.  This is the call the end-to-end benchmark times. c2i only (labels int64 [B]). */
 int vlg_generate_c2i_host(vlg_ctx* ctx, const vlg_generate_params* p, const int64_t* labels_host,

@@ -352,6 +352,42 @@ def generate(geo, w, cond, max_new_tokens, emb_masks=None, cfg_scale=1.0, cfg_in
 
 
 @torch.no_grad()
+def generate_video(geo, w, cond, max_new_tokens, emb_masks=None, cfg_scale=1.0, cfg_interval=-1):
+    """The t2v loop the reference's samplers call (sample_t2v_1f.py:199-205; models/generate_video.py is missing from
+    the fork): generate.py:127-180 with the token hand-off replaced by the latent hand-off of the gpt_video trunk
+    (gpt_video.py:403-431).  Prefill over the caption prefix, CFG mix ``uncond + (cond - uncond) * scale`` of the two
+    output halves (generate.py:95-97; the conditional half alone once ``i > cfg_interval``, :113-114), the mixed latent
+    is the step's output and the next input.  Returns [B, max_new_tokens, vae_embed_dim] in the weights' dtype."""
+    use_cfg = cfg_scale > 1.0
+    dev = cond.device
+    null = torch.zeros_like(cond) + w["cls_embedding.uncond_embedding"]
+    rows = torch.cat([cond, null]) if use_cfg else cond
+    T, B = cond.shape[1], cond.shape[0]
+    R = 2 * B if use_cfg else B
+    dt = w["tok_embeddings.weight"].dtype
+    st = DecodeState(geo, R, T + max_new_tokens, dt, dev)
+    if emb_masks is not None:
+        st.apply_prefix_mask(torch.cat([emb_masks, emb_masks]) if use_cfg else emb_masks)
+
+    def mix(out, guided):
+        if not use_cfg:
+            return out
+        c, u = torch.split(out.float(), B, dim=0)
+        return (u + (c - u) * cfg_scale if guided else c).to(dt)
+
+    lat = mix(forward_latent(geo, w, st, cond=rows, input_pos=torch.arange(T, device=dev))[:, -1], True)
+    seq = [lat]
+    guided = True
+    for i in range(max_new_tokens - 1):
+        if cfg_interval > -1 and i > cfg_interval:
+            guided = False
+        x = (torch.cat([lat, lat]) if use_cfg else lat).unsqueeze(1)
+        lat = mix(forward_latent(geo, w, st, latent=x, input_pos=torch.tensor([T + i], device=dev))[:, -1], guided)
+        seq.append(lat)
+    return torch.stack(seq, dim=1)
+
+
+@torch.no_grad()
 def teacher_forced_logits(geo, w, cond, tokens, emb_masks=None, cfg=True):
     """Per-step raw logits [N, R, V] when the token stream is fixed in advance
     (SURVEY.md 8c item 3): step 0 is the prefill's last position, step i>0 feeds

@@ -148,6 +148,45 @@ def t2v_tiny(refv):
          **{"w." + k: v for k, v in sd_numpy(model).items()})
 
 
+def t2v_generate(refv):
+    """The t2v generation protocol of vlg.generate_video / oracle.generate_video driven through the REFERENCE model's own
+    forward (gpt_video.py:403-431) on the t2v_tiny weights: prefill, CFG mix of the output halves (generate.py:95-97
+    formula), the mixed latent is the next input.  models/generate_video.py itself is missing from the fork."""
+    gv = refv.gpt_video
+    f = np.load(os.path.join(HERE, "t2v_tiny.npz"))
+    args = gv.ModelArgs(dim=128, n_layer=2, n_head=2, vocab_size=64, block_size=16, multiple_of=64,
+                        cls_token_num=120, caption_dim=64, model_type="t2v", vae_embed_dim=8, num_frames=5,
+                        t_downsample_size=4, shuffle_video_tokens=False)
+    model = gv.Transformer(args).eval()
+    model.load_state_dict({k[2:]: torch.from_numpy(f[k]) for k in f.files if k.startswith("w.")}, strict=True)
+    cond, emb_masks = torch.from_numpy(f["cond"]), torch.from_numpy(f["emb_masks"])
+    rows = torch.cat([cond, torch.zeros_like(cond) + model.cls_embedding.uncond_embedding])
+    N, T, B = 24, 120, cond.shape[0]
+    out = {}
+    for name, scale, interval in (("gen", 4.0, -1), ("gen_interval", 4.0, 3)):
+        model.setup_caches(max_batch_size=2 * B, max_seq_length=T + N, dtype=model.tok_embeddings.weight.dtype)
+        m = torch.cat([emb_masks, emb_masks])
+        model.causal_mask[:, :, :T] = model.causal_mask[:, :, :T] * m.unsqueeze(1)
+        eye = torch.eye(model.causal_mask.size(1), model.causal_mask.size(2))
+        model.causal_mask[:] = model.causal_mask * (1 - eye) + eye
+        with torch.no_grad():
+            h, _ = model(idx=None, cond_embed=rows, input_pos=torch.arange(T))
+            c, u = torch.split(h[:, -1], B, dim=0)
+            lat = u + (c - u) * scale
+            seq = [lat]
+            guided = True
+            for i in range(N - 1):
+                if interval > -1 and i > interval:
+                    guided = False
+                x = torch.cat([lat, lat]).unsqueeze(1)
+                h, _ = model(idx=None, cond_embed=None, video_latent=x, input_pos=torch.tensor([T + i]))
+                c, u = torch.split(h[:, -1], B, dim=0)
+                lat = u + (c - u) * scale if guided else c
+                seq.append(lat)
+        out[name] = torch.stack(seq, dim=1).numpy()
+    save("t2v_generate.npz", **out)
+
+
 def sampling(ref):
     g = torch.Generator().manual_seed(21)
     logits = torch.randn(5, 1, 1024, generator=g) * 3
@@ -214,3 +253,5 @@ if __name__ == "__main__":
             gptb(ref)
         if "t2v" in which:
             t2v_tiny(_reference.load(video=True))
+        if "t2vgen" in which:
+            t2v_generate(_reference.load(video=True))

@@ -7,7 +7,7 @@ import torch
 from oracle import ar_decode as O
 from vlg.gpt import Transformer, ModelArgs, GPT_models
 from vlg.generate import generate, prefill, decode_n_tokens, sample
-from helpers import weights_from, TINY_C2I, TINY_T2I
+from helpers import weights_from, TINY_C2I, TINY_T2I, TINY_T2V
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
@@ -221,3 +221,43 @@ def test_t2v_tiny_trunk_adapters_3d_rope(golden):
         # bf16 end to end (weights, activations, cache) vs fp32: relative to the latent scale (|o| ~ 10 in this fixture)
         assert (o16 - o32).abs().max() < 0.03 * o32.abs().max()
         assert (o16 - o32).pow(2).mean().sqrt() < 0.01 * o32.pow(2).mean().sqrt()
+
+
+def test_t2v_generate_loop(golden):
+    """vlg.generate_video.generate (whole loop inside libvlg.so: prefill, adapters, trunk, CFG latent mix, graph replay)
+    against the fixture produced by the reference gpt_video model (fp32), then bf16 against fp32."""
+    from vlg.gpt_video import Transformer as VT, ModelArgs as VArgs
+    from vlg.generate_video import generate as generate_video
+    f, gold = golden("t2v_tiny.npz"), golden("t2v_generate.npz")
+    args = VArgs(dim=128, n_layer=2, n_head=2, vocab_size=64, block_size=16, multiple_of=64, cls_token_num=120,
+                 caption_dim=64, model_type="t2v", vae_embed_dim=8, num_frames=5, t_downsample_size=4,
+                 shuffle_video_tokens=False)
+    m = VT(args).eval()
+    m.load_state_dict({k[2:]: torch.from_numpy(f[k]) for k in f.files if k.startswith("w.")}, strict=True)
+    cond = torch.from_numpy(f["cond"])
+    masks = torch.from_numpy(f["emb_masks"])
+    N = gold["gen"].shape[1]
+    m32 = m.to(DEV, torch.float32)
+    out = generate_video(m32, cond.to(DEV), N, masks.to(DEV), cfg_scale=4.0, temperature=1.0, top_k=0, top_p=1.0,
+                         sample_logits=True)
+    assert out.shape == (2, N, 8) and out.dtype == torch.float32
+    # the fed-back loop of this random-init model is chaotic (fp32 noise grows ~1.6x per step, see the oracle's test):
+    # the first 12 steps pin the protocol
+    K, tol = 12, 2e-3
+    assert np.abs(out.cpu().numpy()[:, :K] - gold["gen"][:, :K]).max() < tol
+    assert np.abs(out.cpu().numpy() - gold["gen"]).max() < 1.0
+    out_i = generate_video(m32, cond.to(DEV), N, masks.to(DEV), cfg_scale=4.0, cfg_interval=3)
+    assert np.abs(out_i.cpu().numpy()[:, :K] - gold["gen_interval"][:, :K]).max() < tol
+    again = generate_video(m32, cond.to(DEV), N, masks.to(DEV), cfg_scale=4.0)          # replayed graph, same result
+    assert torch.equal(out, again)
+    nocfg = generate_video(m32, cond.to(DEV), 6, masks.to(DEV), cfg_scale=1.0)
+    ref_nocfg = O.generate_video(TINY_T2V, weights_from(f, torch.float32, DEV), cond.to(DEV), 6, masks.to(DEV), cfg_scale=1.0)
+    assert (nocfg - ref_nocfg).abs().max() < tol
+    if f["w.cls_embedding.cap_proj.fc1.weight"].shape[1] % 64 == 0:
+        m16 = m.to(DEV, torch.bfloat16)
+        o16 = generate_video(m16, cond.to(DEV), N, masks.to(DEV), cfg_scale=4.0).float()
+        o32 = torch.from_numpy(gold["gen"]).to(DEV)
+        # bf16 end to end with the latent fed back through a chaotic map: the first latent (prefill) must agree, the rest
+        # must stay finite and on the fp32 run's scale
+        assert (o16[:, 0] - o32[:, 0]).abs().max() < 0.03 * o32[:, 0].abs().max()
+        assert torch.isfinite(o16).all() and o16.abs().max() < 2 * o32.abs().max()

@@ -29,7 +29,7 @@ int round8(int n) { return (n + 7) / 8 * 8; }
 
 struct Layout {
   size_t k_cache, v_cache, h, xn, q, attn, ffn, logits, attn_scratch, state, norm_flags, lt_bar, lt_part, mask, seq, labels,
-      cond_rows, prefix_emb, mlp_tmp, total;
+      cond_rows, prefix_emb, mlp_tmp, lat_out, lat_in, total;
 };
 
 Layout make_layout(const vlg_geometry& g, int max_rows, int max_seq) {
@@ -60,6 +60,10 @@ Layout make_layout(const vlg_geometry& g, int max_rows, int max_seq) {
     L.prefix_emb = take((size_t)max_rows * g.cls_token_num * g.dim * e);          // cap_proj output
     L.mlp_tmp = take((size_t)max_rows * g.cls_token_num * g.dim * e);             // fc1 + GELU intermediate
   }
+  if (g.model_type == VLG_T2V) {
+    L.lat_out = take((size_t)max_rows * 16 * ((g.vae_embed_dim + 15) / 16) * e);   // vae_latent_adapter2 output (padded width)
+    L.lat_in = take((size_t)max_rows * 64 * ((g.vae_embed_dim + 63) / 64) * e);    // next input latent (zero-padded width)
+  }
   L.total = off;
   return L;
 }
@@ -83,6 +87,9 @@ struct vlg_ctx {
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   // cached decode-step graph
   cudaGraphExec_t graph = nullptr;
+  cudaGraphExec_t graph_v = nullptr;   // t2v decode step (vlg_generate_t2v)
+  struct KeyV { int rows, B, N, cfg_interval, has_mask; float cfg_scale; void* out; } key_v{};
+  uint64_t step_kernels_v = 0;
   uint64_t step_kernels = 0;   // kernels per replayed decode step
   struct Key { int rows, B, N, top_k, sample_logits, cfg_interval, has_mask; float cfg_scale, temperature, top_p; uint64_t seed; } key{};
 
@@ -120,6 +127,37 @@ __global__ void take_prefix_kernel(const T* __restrict__ emb, T* __restrict__ h,
   const uint4* src = reinterpret_cast<const uint4*>(emb + ((size_t)r * Tn + t) * dim);
   uint4* dst = reinterpret_cast<uint4*>(h + (size_t)r * dim);
   for (int i = threadIdx.x; i < dim * (int)sizeof(T) / 16; i += blockDim.x) dst[i] = src[i];
+}
+
+
+// CFG mix of the output latent (the video counterpart of generate.py:95-99 + the `cur_token = next_token` hand-off):
+// mixed = uncond + (cond - uncond) * scale in fp32 on the T-rounded adapter outputs (cond alone when guidance is off),
+// rounded to T; written to latents[b, step, :] and, zero-padded, to the next input rows b and b + B.  One thread block;
+// the last thread out advances the device loop state.
+template <typename T>
+__global__ void latent_mix_kernel(const T* __restrict__ lat_out, int ld_out, T* __restrict__ lat_in, int ld_in,
+                                  T* __restrict__ latents, int N, int B, int rows, int vae, float cfg_scale,
+                                  int cfg_interval, StepState* st) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int step = st->step;
+  const bool two = rows == 2 * B;
+  const bool guided = two && !(cfg_interval > -1 && step - 1 > cfg_interval);
+  for (int i = threadIdx.x; i < B * vae; i += blockDim.x) {
+    const int b = i / vae, j = i - b * vae;
+    const float c = Num<T>::to_f(lat_out[(size_t)b * ld_out + j]);
+    float x = c;
+    if (guided) {
+      const float u = Num<T>::to_f(lat_out[(size_t)(b + B) * ld_out + j]);
+      x = __fadd_rn(u, __fmul_rn(__fsub_rn(c, u), cfg_scale));
+    }
+    const T xt = Num<T>::from_f(x);
+    latents[((size_t)b * N + step) * vae + j] = xt;
+    lat_in[(size_t)b * ld_in + j] = xt;
+    if (two) lat_in[(size_t)(b + B) * ld_in + j] = xt;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) { st->step = step + 1; st->pos = st->pos + 1; }
 }
 
 // N transformer blocks on ctx->h (in place).  bf16: the RMSNorms are fused into the consuming tensor-core GEMMs (the first
@@ -323,6 +361,7 @@ extern "C" int vlg_ctx_create(const vlg_geometry* g, const vlg_weights* w, int m
 extern "C" void vlg_ctx_destroy(vlg_ctx* c) {
   if (!c) return;
   if (c->graph) cudaGraphExecDestroy(c->graph);
+  if (c->graph_v) cudaGraphExecDestroy(c->graph_v);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
   if (c->ev_fork) cudaEventDestroy(c->ev_fork);
   if (c->ev_join) cudaEventDestroy(c->ev_join);
@@ -513,6 +552,130 @@ static int generate_on(vlg_ctx* c, const vlg_generate_params* pp, const void* co
   if (tokens_dev != c->at<int32_t>(c->L.seq))
     VLG_CUDA(cudaMemcpyAsync(tokens_dev, c->at<int32_t>(c->L.seq), (size_t)p.B * N * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
   return VLG_OK;
+}
+
+
+// ------------------------------------------------------------------------------------------------ t2v generation loop
+namespace {
+
+int launch_latent_mix(vlg_ctx* c, const vlg_generate_params& p, void* latents_dev, int ld_out, int ld_in, cudaStream_t st) {
+  const vlg_geometry& g = c->g;
+  if (g.dtype == VLG_BF16)
+    VLG_CUDA(launch_kernel(latent_mix_kernel<__nv_bfloat16>, dim3(1), dim3(256), 0, st, c->at<const __nv_bfloat16>(c->L.lat_out),
+                           ld_out, c->at<__nv_bfloat16>(c->L.lat_in), ld_in, static_cast<__nv_bfloat16*>(latents_dev),
+                           p.max_new_tokens, p.B, c->rows, g.vae_embed_dim, p.cfg_scale, p.cfg_interval, c->state()));
+  else
+    VLG_CUDA(launch_kernel(latent_mix_kernel<float>, dim3(1), dim3(256), 0, st, c->at<const float>(c->L.lat_out), ld_out,
+                           c->at<float>(c->L.lat_in), ld_in, static_cast<float*>(latents_dev), p.max_new_tokens, p.B, c->rows,
+                           g.vae_embed_dim, p.cfg_scale, p.cfg_interval, c->state()));
+  VLG_LAUNCH_CHECK();
+  return VLG_OK;
+}
+
+// hidden (ctx->xn) -> vae_latent_adapter2 -> CFG mix -> latents[:, step] and the next input; advances step / pos
+int emit_latent(vlg_ctx* c, const vlg_generate_params& p, void* latents_dev, int ld_out, int ld_in, cudaStream_t st) {
+  int rc = vlg_mlp(c, 2, c->at<void>(c->L.xn), c->at<void>(c->L.lat_out), c->rows, st);
+  if (rc) return rc;
+  return launch_latent_mix(c, p, latents_dev, ld_out, ld_in, st);
+}
+
+// next input -> vae_latent_adapter -> trunk at the device-resident position -> emit
+int video_step(vlg_ctx* c, const vlg_generate_params& p, void* latents_dev, int ld_out, int ld_in, int max_pos, cudaStream_t st) {
+  int rc = vlg_mlp(c, 1, c->at<void>(c->L.lat_in), c->at<void>(c->L.h), c->rows, st);
+  if (rc) return rc;
+  if ((rc = run_trunk(c, &c->state()->pos, 0, max_pos, false, st))) return rc;
+  return emit_latent(c, p, latents_dev, ld_out, ld_in, st);
+}
+
+int generate_t2v_on(vlg_ctx* c, const vlg_generate_params* pp, const void* cond_dev, const void* uncond_dev,
+                    const uint8_t* emb_masks_dev, void* latents_dev, cudaStream_t st) {
+  const vlg_generate_params p = *pp;
+  const vlg_geometry& g = c->g;
+  const bool cfg = p.cfg_scale > 1.0f;
+  const int rows = cfg ? 2 * p.B : p.B;
+  const int T = g.cls_token_num, N = p.max_new_tokens;
+  VLG_REQUIRE(p.B > 0 && rows <= c->max_rows, "vlg_generate_t2v: batch %d (rows %d) exceeds max_rows %d", p.B, rows, c->max_rows);
+  VLG_REQUIRE(N > 0 && T + N <= c->S_max && T + N - 1 <= c->w.rope_rows, "vlg_generate_t2v: %d latents do not fit (S_max %d)", N, c->S_max);
+  VLG_REQUIRE(!cfg || uncond_dev, "vlg_generate_t2v: cfg_scale > 1 needs the uncond embedding");
+  VLG_REQUIRE(c->w.cap_fc1 && c->w.adapter_in_fc1 && c->w.adapter_out_fc1, "vlg_generate_t2v: caption / adapter weights missing");
+  const bool bf16 = g.dtype == VLG_BF16;
+  const int ld_out = bf16 ? (g.vae_embed_dim + 15) / 16 * 16 : g.vae_embed_dim;
+  const int ld_in = bf16 ? (g.vae_embed_dim + 63) / 64 * 64 : g.vae_embed_dim;
+  int rc;
+
+  c->rows = rows;
+  c->has_mask = emb_masks_dev != nullptr;
+  if (c->has_mask) {
+    build_mask_rows_kernel<<<(rows * T + 255) / 256, 256, 0, st>>>(emb_masks_dev, c->at<uint8_t>(c->L.mask), p.B, T, rows);
+    VLG_LAUNCH_CHECK();
+  }
+  set_state_kernel<<<1, 1, 0, st>>>(c->state(), 0, T - 1);
+  VLG_LAUNCH_CHECK();
+  VLG_CUDA(cudaMemsetAsync(c->at<void>(c->L.lat_in), 0, (size_t)rows * ld_in * esz(g.dtype), st));   // the padding columns stay zero
+
+  // ---- prefill over the caption prefix (gpt_video.py:403-409), latent 0 from its last position
+  const size_t per_row = (size_t)T * g.caption_dim;
+  void* rows_in = c->at<void>(c->L.cond_rows);
+  dim3 grid(64, rows);
+  if (bf16)
+    build_cond_rows_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)cond_dev, (const __nv_bfloat16*)uncond_dev,
+                                                                (__nv_bfloat16*)rows_in, p.B, per_row);
+  else
+    build_cond_rows_kernel<float><<<grid, 256, 0, st>>>((const float*)cond_dev, (const float*)uncond_dev, (float*)rows_in, p.B, per_row);
+  VLG_LAUNCH_CHECK();
+  if ((rc = vlg_mlp(c, 0, rows_in, c->at<void>(c->L.prefix_emb), rows * T, st))) return rc;
+  for (int t = 0; t < T; ++t) {
+    if (bf16)
+      take_prefix_kernel<__nv_bfloat16><<<rows, 128, 0, st>>>(c->at<__nv_bfloat16>(c->L.prefix_emb), c->at<__nv_bfloat16>(c->L.h), T, t, g.dim);
+    else
+      take_prefix_kernel<float><<<rows, 128, 0, st>>>(c->at<float>(c->L.prefix_emb), c->at<float>(c->L.h), T, t, g.dim);
+    VLG_LAUNCH_CHECK();
+    if ((rc = run_trunk(c, nullptr, t, T + N - 1, false, st))) return rc;
+  }
+  if ((rc = emit_latent(c, p, latents_dev, ld_out, ld_in, st))) return rc;   // step 0 -> 1, pos T-1 -> T
+
+  // ---- decode loop as a replayed CUDA graph
+  if (N > 1) {
+    vlg_ctx::KeyV k{rows, p.B, N, p.cfg_interval, c->has_mask ? 1 : 0, p.cfg_scale, latents_dev};
+    if (!c->graph_v || memcmp(&k, &c->key_v, sizeof(k)) != 0) {
+      if (c->graph_v) { cudaGraphExecDestroy(c->graph_v); c->graph_v = nullptr; }
+      cudaGraph_t graph = nullptr;
+      VLG_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed));
+      const uint64_t before = vlg_launch_count();
+      rc = video_step(c, p, latents_dev, ld_out, ld_in, T + N - 1, st);
+      const uint64_t after = vlg_launch_count();
+      count_launches(before - after);
+      cudaError_t e = cudaStreamEndCapture(st, &graph);
+      if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+      VLG_CUDA(e);
+      e = cudaGraphInstantiate(&c->graph_v, graph, 0);
+      cudaGraphDestroy(graph);
+      VLG_CUDA(e);
+      memset(&c->key_v, 0, sizeof(c->key_v));
+      c->key_v = k;
+      c->step_kernels_v = after - before;
+    }
+    for (int i = 0; i < N - 1; ++i) VLG_CUDA(cudaGraphLaunch(c->graph_v, st));
+    count_launches((uint64_t)(N - 1) * c->step_kernels_v);
+  }
+  return VLG_OK;
+}
+
+}  // namespace
+
+extern "C" int vlg_generate_t2v(vlg_ctx* c, const vlg_generate_params* pp, const void* cond_dev, const void* uncond_dev,
+                                const uint8_t* emb_masks_dev, void* latents_dev, void* stream) {
+  VLG_REQUIRE(c && pp && cond_dev && latents_dev, "vlg_generate_t2v: null pointer");
+  VLG_REQUIRE(c->g.model_type == VLG_T2V, "vlg_generate_t2v: model type %d is not t2v", c->g.model_type);
+  cudaStream_t user = (cudaStream_t)stream;
+  const bool legacy = user == nullptr || user == cudaStreamLegacy || user == cudaStreamPerThread;
+  if (!legacy) return generate_t2v_on(c, pp, cond_dev, uncond_dev, emb_masks_dev, latents_dev, user);
+  VLG_CUDA(cudaEventRecord(c->ev_fork, user));
+  VLG_CUDA(cudaStreamWaitEvent(c->own_stream, c->ev_fork, 0));
+  int rc = generate_t2v_on(c, pp, cond_dev, uncond_dev, emb_masks_dev, latents_dev, c->own_stream);
+  VLG_CUDA(cudaEventRecord(c->ev_join, c->own_stream));
+  VLG_CUDA(cudaStreamWaitEvent(user, c->ev_join, 0));
+  return rc;
 }
 
 extern "C" int vlg_generate_c2i_host(vlg_ctx* c, const vlg_generate_params* p, const int64_t* labels_host,

@@ -56,6 +56,7 @@ SIGNATURES = {
     "vlg_forward_pos": (_I, [_P, _P, _P, _P, _I, _P, _P, _P]),
     "vlg_mlp": (_I, [_P, _I, _P, _P, _I, _P]),
     "vlg_generate": (_I, [_P, C.POINTER(GenerateParams), _P, _P, _P, _P, _P]),
+    "vlg_generate_t2v": (_I, [_P, C.POINTER(GenerateParams), _P, _P, _P, _P, _P]),
     "vlg_generate_c2i_host": (_I, [_P, C.POINTER(GenerateParams), _P, _P, _P]),
     "vlg_rmsnorm": (_I, [_P, _P, _P, _I, _I, _F, _I, _P]),
     "vlg_linear": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P]),

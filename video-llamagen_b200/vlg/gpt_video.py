@@ -82,6 +82,20 @@ class VideoEngine(Engine):
         w.adapter_out_fc1 = dev(model.vae_latent_adapter2.fc1.weight)
         w.adapter_out_fc2 = dev(fc2_out)
 
+    def generate_video(self, cond, max_new_tokens, emb_masks, cfg_scale, cfg_interval):
+        """Whole t2v loop inside libvlg.so -> latents [B, max_new_tokens, vae_embed_dim] (model dtype)."""
+        import ctypes as C
+        B = cond.shape[0]
+        gp = L.GenerateParams(B, int(max_new_tokens), float(cfg_scale), int(cfg_interval), 1.0, 0, 1.0, 0, 0)
+        out = torch.empty(B, max_new_tokens, self.geo.vae_embed_dim, dtype=self.dtype, device=self.device)
+        masks = None
+        if emb_masks is not None:
+            masks = emb_masks.to(self.device).ne(0).to(torch.uint8).contiguous()
+        with torch.cuda.device(self.device):
+            L.check(L.lib().vlg_generate_t2v(self.ctx, C.byref(gp), L.ptr(cond), L.ptr(self.uncond), L.ptr(masks), L.ptr(out),
+                                             L.stream()))
+        return out
+
     def adapter_in(self, latent):
         x = latent.to(self.dtype)
         if self.dtype == torch.bfloat16:
