@@ -24,7 +24,7 @@ import sys
 import threading
 import time
 
-os.environ.setdefault("NCCL_DEBUG", "WARN")   # keep NCCL's version banner off stdout: the contract is ONE JSON line
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL's version banner / debug lines go to stderr: stdout carries ONE JSON line
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 for p in (ROOT, os.path.join(ROOT, "video-llamagen_b200")):

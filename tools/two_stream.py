@@ -36,7 +36,7 @@ def run(parts):
     torch.cuda.empty_cache()
     return dt
 
-for n in (1, 2, 4):
+for n in (1, 2):
     parts = list(cond.chunk(n))
     dt = run(parts)
     print(f"{n} concurrent sub-batches: {dt*1e3:8.1f} ms per generate -> {64*N/dt:9.0f} tok/s", flush=True)

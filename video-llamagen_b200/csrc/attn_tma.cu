@@ -19,13 +19,19 @@ namespace vlg {
 
 constexpr int kTile = 32;                   // cache positions per TMA tile
 constexpr int kCW = 8;                      // consumer warps
-constexpr int kStagesA = 16;                // ring depth (multiple of kCW: stage s always belongs to warp s % kCW)
+#ifndef VLG_ATTN_STAGES
+#define VLG_ATTN_STAGES 16
+#endif
+#ifndef VLG_ATTN_SLOTS
+#define VLG_ATTN_SLOTS 16
+#endif
+constexpr int kStagesA = VLG_ATTN_STAGES;    // ring depth (multiple of kCW: stage s always belongs to warp s % kCW)
 constexpr int kTileBytes = kTile * 128;     // one K or V tile (D = 64 bf16 = 128 B per position)
 constexpr int kStageBytesA = 2 * kTileBytes;
 constexpr int kAttnTmaThreads = (kCW + 2) * 32;     // consumers, TMA producer (warp kCW), merger (warp kCW + 1)
 constexpr int kMaxSplitsT = 32;
 
-constexpr int kSlots = 16;                  // in-flight work items per CTA whose partial states await their merge
+constexpr int kSlots = VLG_ATTN_SLOTS;       // in-flight work items per CTA whose partial states await their merge
 
 // Explicit shared-space accesses: the ring lives behind a manually aligned pointer, which makes the compiler fall back
 // to generic LD/ST (slower address-space resolution on every access) unless the state space is spelled out.

@@ -25,8 +25,16 @@
 
 namespace vlg {
 
-constexpr int kLtThreads = 384;            // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-9: TMEM readers (two per lane quadrant); all: row phases
-constexpr int kLtStages = 6;
+#ifndef VLG_LT_THREADS
+#define VLG_LT_THREADS 384
+#endif
+#ifndef VLG_LT_STAGES
+#define VLG_LT_STAGES 6
+#endif
+constexpr int kLtThreads = VLG_LT_THREADS;            // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-9: TMEM readers (two per lane quadrant); all: row phases
+constexpr int kLtStages = VLG_LT_STAGES;
+constexpr int kLtReaders = (kLtThreads / 32 - 2) >= 8 ? 8 : 4;   // TMEM reader warps: two per lane quadrant when the block has them
+constexpr int kLtHalves = kLtReaders / 4;
 constexpr int kLtABytes = 128 * 64 * 2;    // activation tile: 128 rows x 64 k
 constexpr int kLtStageBytes = 2 * kLtABytes;   // + weight tile of up to 128 rows x 64 k
 constexpr int kLtTmemCols = 128;
@@ -195,7 +203,7 @@ __device__ __forceinline__ void lt_gemm_phase(const LtGemm& G, const TensorMap* 
       umma_commit(&sm.acc_ready);
     }
     __syncwarp();
-  } else if (warp < 10) {
+  } else if (warp < 2 + kLtReaders) {
     if (u.valid) {
       // TMEM lane quadrant = warp % 4 (hardware rule); the two warps of a quadrant split the columns.  Every store below
       // covers whole 32-byte sectors: partial-sector writes cost the L2 several times their size.
@@ -206,7 +214,7 @@ __device__ __forceinline__ void lt_gemm_phase(const LtGemm& G, const TensorMap* 
       if (threadIdx.x == 64) LT_TS_AT(ts_slot);
       if constexpr (MODE < 0) {
         float* dst = P.part + ((size_t)u.split * P.rows + r) * G.N + u.n0;
-        for (int c = half * 16; c < G.BN; c += 32) {
+        for (int c = half * 16; c < G.BN; c += 16 * kLtHalves) {
           float v[16];
           tmem_ld16(lane_base + c, v);
           if (r < P.rows) {
@@ -215,7 +223,7 @@ __device__ __forceinline__ void lt_gemm_phase(const LtGemm& G, const TensorMap* 
           }
         }
       } else if constexpr (MODE == EPI_SWIGLU) {      // gpt.py:167 -- w1/w3 rows interleaved: columns (2j, 2j+1) = (w1 x, w3 x)_j
-        for (int c = half * 32; c < G.BN; c += 64) {
+        for (int c = half * 32; c < G.BN; c += 32 * kLtHalves) {
           float v[32];
           tmem_ld16(lane_base + c, v);
           tmem_ld16(lane_base + c + 16, v + 16);
@@ -231,7 +239,7 @@ __device__ __forceinline__ void lt_gemm_phase(const LtGemm& G, const TensorMap* 
         }
       } else {                                         // EPI_QKV_ROPE on 16 columns (a quarter head): gpt.py:215-227, 423-433, 177-185
         const int pos = E.pos_ptr ? *E.pos_ptr : E.pos_imm;
-        for (int c = half * 16; c < G.BN; c += 32) {
+        for (int c = half * 16; c < G.BN; c += 16 * kLtHalves) {
           float v[16];
           tmem_ld16(lane_base + c, v);
           if (r < P.rows) {
