@@ -261,3 +261,31 @@ def test_t2v_generate_loop(golden):
         # must stay finite and on the fp32 run's scale
         assert (o16[:, 0] - o32[:, 0]).abs().max() < 0.03 * o32[:, 0].abs().max()
         assert torch.isfinite(o16).all() and o16.abs().max() < 2 * o32.abs().max()
+
+
+def test_batched_prefill_equals_stepped_prefill(golden):
+    """The batched T = 120 prefill (real GEMMs over rows * T, causal prefix attention, one launch set per layer) against
+    the position-by-position prefill it replaces (VLG_STEPPED_PREFILL=1, read once per process -> subprocesses): same
+    greedy tokens for the masked t2i fixture in fp32, and the fixture's own tokens."""
+    import os, subprocess, sys, json
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import sys, json, numpy as np, torch\n"
+        f"sys.path[:0] = [{root!r}, {os.path.join(root, 'video-llamagen_b200')!r}, {os.path.join(root, 'tests')!r}]\n"
+        "from vlg.gpt import Transformer, ModelArgs\n"
+        "from vlg.generate import generate\n"
+        f"f = np.load({os.path.join(root, 'tests', 'golden', 't2i_tiny.npz')!r})\n"
+        f"m = Transformer(ModelArgs(**{T2I_ARGS!r})).eval()\n"
+        "m.load_state_dict({k[2:]: torch.from_numpy(f[k]) for k in f.files if k.startswith('w.')}, strict=True)\n"
+        "m = m.to('cuda')\n"
+        "cond = torch.from_numpy(f['cond']).cuda(); masks = torch.from_numpy(f['emb_masks']).cuda()\n"
+        "g = generate(m, cond, 16, masks, cfg_scale=4.0, temperature=1.0, top_k=1, top_p=1.0, sample_logits=False)\n"
+        "print(json.dumps(g.cpu().tolist()))\n")
+    outs = []
+    for stepped in ("0", "1"):
+        env = dict(os.environ, VLG_STEPPED_PREFILL=stepped)
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs.append(json.loads(r.stdout.strip().splitlines()[-1]))
+    assert outs[0] == outs[1]
+    assert np.array_equal(np.array(outs[0]), golden("t2i_tiny.npz")["greedy"])

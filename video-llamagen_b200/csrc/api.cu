@@ -29,7 +29,7 @@ int round8(int n) { return (n + 7) / 8 * 8; }
 
 struct Layout {
   size_t k_cache, v_cache, h, xn, q, attn, ffn, logits, attn_scratch, state, norm_flags, lt_bar, lt_part, mask, seq, labels,
-      cond_rows, prefix_emb, mlp_tmp, lat_out, lat_in, total;
+      cond_rows, prefix_emb, mlp_tmp, q_p, attn_p, ffn_p, lat_out, lat_in, total;
 };
 
 Layout make_layout(const vlg_geometry& g, int max_rows, int max_seq) {
@@ -58,7 +58,10 @@ Layout make_layout(const vlg_geometry& g, int max_rows, int max_seq) {
   if (g.model_type != VLG_C2I) {
     L.cond_rows = take((size_t)max_rows * g.cls_token_num * g.caption_dim * e);   // raw condition rows (cond + uncond)
     L.prefix_emb = take((size_t)max_rows * g.cls_token_num * g.dim * e);          // cap_proj output
-    L.mlp_tmp = take((size_t)max_rows * g.cls_token_num * g.dim * e);             // fc1 + GELU intermediate
+    L.mlp_tmp = take((size_t)max_rows * g.cls_token_num * g.dim * e);             // fc1 + GELU intermediate; normed hidden of the batched prefill
+    L.q_p = take((size_t)max_rows * g.cls_token_num * g.dim * e);                 // batched prefill: q, attention output, SwiGLU output
+    L.attn_p = take((size_t)max_rows * g.cls_token_num * g.dim * e);              //   for all T prefix positions of every row at once
+    L.ffn_p = take((size_t)max_rows * g.cls_token_num * g.hidden_dim * e);
   }
   if (g.model_type == VLG_T2V) {
     L.lat_out = take((size_t)max_rows * 16 * ((g.vae_embed_dim + 15) / 16) * e);   // vae_latent_adapter2 output (padded width)
@@ -255,6 +258,57 @@ int run_trunk(vlg_ctx* c, const int* pos_ptr, int pos_imm, int max_pos, bool fus
   }
   if (fuse && fuse_final) return VLG_OK;
   return launch_rmsnorm(g.dtype, h, c->w.norm, xn, R, d, g.norm_eps, st);
+}
+
+
+// All T conditioning positions of every row through the trunk AT ONCE (gpt.py:351-352 with the reference's batched
+// prefill shapes: M = rows * T real GEMM rows, causal attention inside the prefix with emb_masks).  The residual stream
+// is ctx->prefix_emb [rows, T, dim] in place; K/V of positions 0..T-1 land in the caches; on return ctx->xn holds the
+// final-normed hidden state of the LAST prefix position of every row (the only one generate() uses, generate.py:84-86:
+// the reference also computes -- and discards -- logits for the other T-1 positions).
+int run_trunk_prefix(vlg_ctx* c, int T, cudaStream_t st) {
+  const vlg_geometry& g = c->g;
+  const int R = c->rows, M = R * T, d = g.dim, hid = g.hidden_dim;
+  void* hp = c->at<void>(c->L.prefix_emb);
+  void* xnp = c->at<void>(c->L.mlp_tmp);
+  void* qp = c->at<void>(c->L.q_p);
+  void* attnp = c->at<void>(c->L.attn_p);
+  void* ffnp = c->at<void>(c->L.ffn_p);
+  int rc;
+  for (int l = 0; l < g.n_layer; ++l) {
+    const vlg_layer_weights& lw = c->layers[l];
+    if ((rc = launch_rmsnorm(g.dtype, hp, lw.attention_norm, xnp, M, d, g.norm_eps, st))) return rc;
+    EpiParams P{};
+    P.q_out = qp; P.k_cache = c->kc(l); P.v_cache = c->vc(l);
+    P.rope = c->w.rope_table; P.pos_ptr = nullptr; P.pos_imm = 0;
+    P.S_max = c->S_max; P.H = g.n_head; P.D = c->D; P.dim = d;
+    P.q_per_row = T;
+    if ((rc = launch_gemm(g.dtype, EPI_QKV_ROPE, xnp, lw.wqkv, M, 3 * d, d, P, st))) return rc;
+    AttnArgs a{};
+    a.q = qp; a.k_cache = c->kc(l); a.v_cache = c->vc(l); a.out = attnp;
+    a.rows = R; a.H = g.n_head; a.D = c->D; a.S_max = c->S_max;
+    a.pos_ptr = nullptr; a.pos_imm = 0; a.max_pos = T - 1;
+    a.prefix_mask = c->has_mask ? c->at<uint8_t>(c->L.mask) : nullptr;
+    a.T_prefix = c->has_mask ? g.cls_token_num : 0;
+    a.q_per_row = T;
+    if ((rc = launch_attn_generic(g.dtype, a, st))) return rc;
+    EpiParams Po{};
+    Po.out = hp; Po.ld_out = d; Po.resid = hp;
+    if ((rc = launch_gemm(g.dtype, EPI_RESID, attnp, lw.wo, M, d, d, Po, st))) return rc;
+    if ((rc = launch_rmsnorm(g.dtype, hp, lw.ffn_norm, xnp, M, d, g.norm_eps, st))) return rc;
+    EpiParams Pf{};
+    Pf.out = ffnp; Pf.ld_out = hid;
+    if ((rc = launch_gemm(g.dtype, EPI_SWIGLU, xnp, lw.w13, M, 2 * hid, d, Pf, st))) return rc;
+    EpiParams P2{};
+    P2.out = hp; P2.ld_out = d; P2.resid = hp;
+    if ((rc = launch_gemm(g.dtype, EPI_RESID, ffnp, lw.w2, M, d, hid, P2, st))) return rc;
+  }
+  if (g.dtype == VLG_BF16)
+    take_prefix_kernel<__nv_bfloat16><<<R, 128, 0, st>>>(static_cast<const __nv_bfloat16*>(hp), c->at<__nv_bfloat16>(c->L.h), T, T - 1, d);
+  else
+    take_prefix_kernel<float><<<R, 128, 0, st>>>(static_cast<const float*>(hp), c->at<float>(c->L.h), T, T - 1, d);
+  VLG_LAUNCH_CHECK();
+  return launch_rmsnorm(g.dtype, c->at<void>(c->L.h), c->w.norm, c->at<void>(c->L.xn), R, d, g.norm_eps, st);
 }
 
 int run_head(vlg_ctx* c, float* logits, bool fused_final_norm, cudaStream_t st) {
@@ -505,13 +559,18 @@ static int generate_on(vlg_ctx* c, const vlg_generate_params* pp, const void* co
       build_cond_rows_kernel<float><<<grid, 256, 0, st>>>((const float*)cond_dev, (const float*)uncond_dev, (float*)rows_in, p.B, per_row);
     VLG_LAUNCH_CHECK();
     if ((rc = vlg_mlp(c, 0, rows_in, c->at<void>(c->L.prefix_emb), rows * T, st))) return rc;
-    for (int t = 0; t < T; ++t) {
-      if (g.dtype == VLG_BF16)
-        take_prefix_kernel<__nv_bfloat16><<<rows, 128, 0, st>>>(c->at<__nv_bfloat16>(c->L.prefix_emb), c->at<__nv_bfloat16>(c->L.h), T, t, g.dim);
-      else
-        take_prefix_kernel<float><<<rows, 128, 0, st>>>(c->at<float>(c->L.prefix_emb), c->at<float>(c->L.h), T, t, g.dim);
-      VLG_LAUNCH_CHECK();
-      if ((rc = run_trunk(c, nullptr, t, T + N - 1, t == T - 1, st))) return rc;
+    static const bool stepped = [] { const char* e = getenv("VLG_STEPPED_PREFILL"); return e && e[0] == '1'; }();   // A/B
+    if (!stepped) {
+      if ((rc = run_trunk_prefix(c, T, st))) return rc;
+    } else {
+      for (int t = 0; t < T; ++t) {
+        if (g.dtype == VLG_BF16)
+          take_prefix_kernel<__nv_bfloat16><<<rows, 128, 0, st>>>(c->at<__nv_bfloat16>(c->L.prefix_emb), c->at<__nv_bfloat16>(c->L.h), T, t, g.dim);
+        else
+          take_prefix_kernel<float><<<rows, 128, 0, st>>>(c->at<float>(c->L.prefix_emb), c->at<float>(c->L.h), T, t, g.dim);
+        VLG_LAUNCH_CHECK();
+        if ((rc = run_trunk(c, nullptr, t, T + N - 1, t == T - 1, st))) return rc;
+      }
     }
   }
   if ((rc = run_head(c, c->at<float>(c->L.logits), true, st))) return rc;
@@ -624,13 +683,18 @@ int generate_t2v_on(vlg_ctx* c, const vlg_generate_params* pp, const void* cond_
     build_cond_rows_kernel<float><<<grid, 256, 0, st>>>((const float*)cond_dev, (const float*)uncond_dev, (float*)rows_in, p.B, per_row);
   VLG_LAUNCH_CHECK();
   if ((rc = vlg_mlp(c, 0, rows_in, c->at<void>(c->L.prefix_emb), rows * T, st))) return rc;
-  for (int t = 0; t < T; ++t) {
-    if (bf16)
-      take_prefix_kernel<__nv_bfloat16><<<rows, 128, 0, st>>>(c->at<__nv_bfloat16>(c->L.prefix_emb), c->at<__nv_bfloat16>(c->L.h), T, t, g.dim);
-    else
-      take_prefix_kernel<float><<<rows, 128, 0, st>>>(c->at<float>(c->L.prefix_emb), c->at<float>(c->L.h), T, t, g.dim);
-    VLG_LAUNCH_CHECK();
-    if ((rc = run_trunk(c, nullptr, t, T + N - 1, false, st))) return rc;
+  static const bool stepped = [] { const char* e = getenv("VLG_STEPPED_PREFILL"); return e && e[0] == '1'; }();   // A/B
+  if (!stepped) {
+    if ((rc = run_trunk_prefix(c, T, st))) return rc;
+  } else {
+    for (int t = 0; t < T; ++t) {
+      if (bf16)
+        take_prefix_kernel<__nv_bfloat16><<<rows, 128, 0, st>>>(c->at<__nv_bfloat16>(c->L.prefix_emb), c->at<__nv_bfloat16>(c->L.h), T, t, g.dim);
+      else
+        take_prefix_kernel<float><<<rows, 128, 0, st>>>(c->at<float>(c->L.prefix_emb), c->at<float>(c->L.h), T, t, g.dim);
+      VLG_LAUNCH_CHECK();
+      if ((rc = run_trunk(c, nullptr, t, T + N - 1, false, st))) return rc;
+    }
   }
   if ((rc = emit_latent(c, p, latents_dev, ld_out, ld_in, st))) return rc;   // step 0 -> 1, pos T-1 -> T
 

@@ -31,16 +31,20 @@ template <typename T, int D>
 __global__ void __launch_bounds__(kAttnThreads)
 attn_decode_generic_kernel(const T* __restrict__ q, const T* __restrict__ kc, const T* __restrict__ vc,
                            T* __restrict__ out, float* __restrict__ part, int H, int S_max, const int* pos_ptr,
-                           int pos_imm, const uint8_t* __restrict__ mask, int T_prefix, int n_splits) {
+                           int pos_imm, const uint8_t* __restrict__ mask, int T_prefix, int n_splits, int q_per_row) {
   static_assert(D == 64, "head_dim 64");
   constexpr int E = D / 8;  // elements per lane
   __shared__ float s_m[kAttnThreads / 32], s_l[kAttnThreads / 32], s_o[kAttnThreads / 32][D];
 
   const int rh = blockIdx.x, split = blockIdx.y;
-  const int row = rh / H;
   pdl_launch_dependents();
   pdl_wait();
-  const int pos = pos_ptr ? *pos_ptr : pos_imm;
+  // decode: query row == cache row, one position for all.  Batched prefill (q_per_row > 0): query row qr is position
+  // pos_imm + qr % q_per_row of cache row qr / q_per_row.
+  const int qr = rh / H, head = rh - qr * H;
+  const int row = q_per_row > 0 ? qr / q_per_row : qr;
+  const int pos = q_per_row > 0 ? pos_imm + (qr - row * q_per_row) : (pos_ptr ? *pos_ptr : pos_imm);
+  const size_t kv_rh = (size_t)row * H + head;
   const int n = pos + 1;
   int chunk = (n + n_splits - 1) / n_splits;
   chunk = (chunk + 15) & ~15;
@@ -55,8 +59,8 @@ attn_decode_generic_kernel(const T* __restrict__ q, const T* __restrict__ kc, co
 #pragma unroll
   for (int i = 0; i < E; ++i) qf[i] = __fmul_rn(qf[i], scale);
 
-  const T* kbase = kc + (size_t)rh * S_max * D + c * E;
-  const T* vbase = vc + (size_t)rh * S_max * D + c * E;
+  const T* kbase = kc + kv_rh * S_max * D + c * E;
+  const T* vbase = vc + kv_rh * S_max * D + c * E;
   const uint8_t* mrow = mask ? mask + (size_t)row * T_prefix : nullptr;
 
   float m = -INFINITY, l = 0.f, acc[E];
@@ -166,15 +170,15 @@ static int pick_splits(int rh, int max_pos) {
 
 template <typename T>
 static int launch_typed(const AttnArgs& a, cudaStream_t st) {
-  const int rh = a.rows * a.H;
-  int n_splits = pick_splits(rh, a.max_pos);
+  const int rh = a.rows * a.H * (a.q_per_row > 0 ? a.q_per_row : 1);
+  int n_splits = a.q_per_row > 0 ? 1 : pick_splits(rh, a.max_pos);
   if (n_splits > 1) {
     VLG_REQUIRE(a.scratch && a.scratch_bytes >= (size_t)rh * n_splits * (a.D + 2) * sizeof(float),
                 "attn: scratch too small for %d splits", n_splits);
   }
   VLG_CUDA(launch_kernel(attn_decode_generic_kernel<T, 64>, dim3(rh, n_splits), dim3(kAttnThreads), 0, st, (const T*)a.q,
                          (const T*)a.k_cache, (const T*)a.v_cache, (T*)a.out, a.scratch, a.H, a.S_max, a.pos_ptr,
-                         a.pos_imm, a.prefix_mask, a.T_prefix, n_splits));
+                         a.pos_imm, a.prefix_mask, a.T_prefix, n_splits, a.q_per_row));
   VLG_LAUNCH_CHECK();
   if (n_splits > 1) {
     VLG_CUDA(launch_kernel(attn_combine_kernel<T, 64>, dim3(rh), dim3(64), 0, st, (const float*)a.scratch, (T*)a.out, n_splits));

@@ -28,6 +28,8 @@ struct EpiParams {
   const int* pos_ptr;   // device scalar with the cache slot, or nullptr -> pos_imm
   int pos_imm;
   int S_max, H, D, dim;
+  int q_per_row;        // batched prefill: GEMM row r is query (r % q_per_row) of cache row (r / q_per_row) at position
+                        // pos_imm + r % q_per_row; 0 = decode (row r is cache row r at the scalar position)
   // Fused RMSNorm prologue (bf16 tensor-core GEMM only; norm_flag == nullptr -> the A operand is used as given).
   // The first CTAs of the grid normalise `norm_src` into the A buffer (the tensor map's base) and publish a counter;
   // every CTA's producer waits on it before loading A.  Same arithmetic as rmsnorm_kernel (gpt.py:143-148).
@@ -97,7 +99,13 @@ __device__ __forceinline__ void epi8(int r, int n0, const float* v, const EpiPar
       dst[i] = Num<T>::from_f(__fmul_rn(s, b));
     }
   } else if constexpr (EPI == EPI_QKV_ROPE) {
-    const int pos = P.pos_ptr ? *P.pos_ptr : P.pos_imm;
+    int pos, rc = r;
+    if (P.q_per_row > 0) {
+      rc = r / P.q_per_row;
+      pos = P.pos_imm + (r - rc * P.q_per_row);
+    } else {
+      pos = P.pos_ptr ? *P.pos_ptr : P.pos_imm;
+    }
     const int sec = n0 / P.dim, c = n0 - sec * P.dim;
     const int head = c / P.D, dd = c - head * P.D;
     float o[8];
@@ -119,7 +127,7 @@ __device__ __forceinline__ void epi8(int r, int n0, const float* v, const EpiPar
       store8<T>(static_cast<T*>(P.q_out) + (size_t)r * P.dim + c, o);
     } else {
       T* cache = static_cast<T*>(sec == 1 ? P.k_cache : P.v_cache);
-      store8<T>(cache + (((size_t)r * P.H + head) * P.S_max + pos) * P.D + dd, o);
+      store8<T>(cache + (((size_t)rc * P.H + head) * P.S_max + pos) * P.D + dd, o);
     }
   }
 }

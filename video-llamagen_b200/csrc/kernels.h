@@ -28,6 +28,8 @@ struct AttnArgs {
   float* scratch;       // split partials
   size_t scratch_bytes;
   int max_pos;          // upper bound of pos over the life of a captured graph (sizes the split count)
+  int q_per_row;        // generic kernel only, batched prefill: q / out hold q_per_row queries per cache row (positions
+                        // pos_imm .. pos_imm + q_per_row - 1); 0 = one query per cache row
 };
 int launch_attn_generic(int dtype, const AttnArgs& a, cudaStream_t st);
 size_t attn_scratch_bytes(int rows, int H, int D, int S_max);
