@@ -158,7 +158,8 @@ def test_gptl_cfg2_full_size_bf16():
     assert rms_ours <= 1.5 * rms_ref + 1e-4, (rms_ours, rms_ref)       # no noisier than the reference's own bf16 run
 
 
-@pytest.mark.parametrize("name,n_layer,B", [("GPT-B", 3, 4), ("GPT-XL", 2, 8), ("GPT-XXL", 2, 32), ("GPT-1B", 2, 64)])
+@pytest.mark.parametrize("name,n_layer,B", [("GPT-B", 3, 4), ("GPT-XL", 2, 8), ("GPT-XXL", 2, 32), ("GPT-1B", 2, 64),
+                                            ("GPT-B", 2, 80)])   # 160 rows: beyond the layer-tail kernel, per-op kernels
 def test_layer_tail_geometries_bf16(name, n_layer, B):
     """The persistent layer-tail kernel (split-K tile shapes, ring wrap-around, row phases) at the widths of the other
     registry entries -- d = 768 / 1280 / 1536 / 2048, hidden 2048 / 3584 / 4096 / 5632, 8..128 cache rows -- on a few
