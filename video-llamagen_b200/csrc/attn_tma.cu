@@ -178,8 +178,16 @@ attn_decode_tma_kernel(const __grid_constant__ TensorMap tmK, const __grid_const
   const float kScale = 0.125f * 1.4426950408889634f;   // 1/sqrt(64) * log2(e)
   uint32_t gt0 = 0;                                     // tiles issued before the current item
   int item_i = 0;
+  // this lane's two query elements, fetched one item ahead: the L2 round trip of the query would otherwise sit in front
+  // of every item's first tile (items are 1-19 tiles long, a warp owns 1-3 of them)
+  uint32_t qw_next = 0;
+  if ((int)blockIdx.x < n_items)
+    qw_next = *reinterpret_cast<const uint32_t*>(q + (size_t)(blockIdx.x / n_splits) * 64 + 2 * lane);
   for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++item_i) {
     const int rh = item / n_splits, split = item - rh * n_splits;
+    const uint32_t qw = qw_next;
+    if (item + (int)gridDim.x < n_items)
+      qw_next = *reinterpret_cast<const uint32_t*>(q + (size_t)((item + gridDim.x) / n_splits) * 64 + 2 * lane);
     const int s_begin = split * chunk, s_end = min(n, s_begin + chunk);
     const int n_tiles = s_end > s_begin ? (s_end - s_begin + kTile - 1) / kTile : 0;
     const int w0 = (int)(gt0 % kCW);                                  // warp that owns the item's first tile
@@ -194,7 +202,6 @@ attn_decode_tma_kernel(const __grid_constant__ TensorMap tmK, const __grid_const
     // broadcast reads (one wavefront each) are cheaper than the register pressure they remove (measured 1-3 % faster).
     const uint32_t q_base = smem_u32(&sm.q[warp][0]);
     {
-      const uint32_t qw = *reinterpret_cast<const uint32_t*>(q + (size_t)rh * 64 + 2 * lane);
       __syncwarp();                                       // previous item's readers of sm.q are done
       sts32f(q_base + lane * 8, bf16lo(qw) * kScale);
       sts32f(q_base + lane * 8 + 4, bf16hi(qw) * kScale);
