@@ -8,14 +8,18 @@
 // ~64 B/clk L2 port (profiles/README.md).  Here one CTA per SM stays resident and the step is a sequence of phases
 // separated by grid barriers (one L2 atomic + one polled load, all CTAs co-resident by construction):
 //
-//   * GEMM phases are split-K: a unit = (BN-wide column tile, K slice), at most one unit per CTA, chosen on the host so
-//     that (nearly) every SM owns one and ingests only its [128 x K/S] activation slice + [BN x K/S] weight slice through
-//     TMA (128B swizzle) into a 6-stage ring; one elected thread issues tcgen05.mma (M=128, N=BN, K=16) into a TMEM
-//     accumulator; four warps read it back (tcgen05.ld) and store the fp32 PARTIAL tile to an L2-resident scratch
-//     with 256-bit stores.  The weight tiles of the NEXT GEMM phase are requested as soon as the ring has room, i.e.
-//     while this phase's epilogue, the barrier and the row phase in between run: weights never wait on HBM latency.
-//   * Row phases reduce the S partials in a fixed order (deterministic) and apply the reference's elementwise tail with
-//     its exact rounding points (epilogue.cuh): residual add + RMSNorm (one row per CTA), SwiGLU, RoPE + cache append.
+//   * GEMM phases: a unit = (BN-wide column tile, K slice), at most one unit per CTA, chosen on the host (lt_pick) from
+//     the bytes a CTA pulls through its L2 port.  Operands arrive through TMA (128B swizzle) in a 6-stage ring, one
+//     elected thread issues tcgen05.mma (M = 128 rows, N = BN, K = 16) into a TMEM accumulator, eight warps (two per TMEM
+//     lane quadrant) read it back with tcgen05.ld.
+//       - wo and w2 are split-K (their residual + RMSNorm row phase follows anyway): every SM ingests only its
+//         [128 x K/S] activation slice and stores the fp32 PARTIAL tile to an L2-resident scratch with 256-bit stores;
+//       - w1|w3 and wqkv own all of K and apply SwiGLU / RoPE + cache append straight from TMEM with 32-byte stores
+//         (split-K here would cost two more barriers and 13 MB more partial traffic than it saves in ingest).
+//     The weight tiles of the NEXT GEMM phase are requested as soon as the ring has room, i.e. while this phase's
+//     epilogue, the barrier and the row phase in between run: weights never wait on HBM latency.
+//   * Row phase (one row per CTA): fixed-order reduction of the S partials (deterministic), residual add and RMSNorm with
+//     the reference's rounding points (epilogue.cuh / elementwise.cu).
 //
 // Only the tensor-core tile is re-shaped; no arithmetic of the reference is re-associated except the fp32 K-sum order.
 #include <stdlib.h>
@@ -42,7 +46,7 @@ constexpr int kLtSmemBytes = kLtStages * kLtStageBytes + 1024 /*align slack*/ + 
 
 struct LtGemm {
   int N, K;        // out features, in features
-  int BN;          // column tile (64 or 128)
+  int BN;          // column tile (32, 64 or 128)
   int S;           // K splits
   int n_tiles;     // N / BN
   int kb_per;      // 64-wide k-blocks per split (the last split may own fewer)
