@@ -206,6 +206,7 @@ int run_trunk(vlg_ctx* c, const int* pos_ptr, int pos_imm, int max_pos, bool fus
       a.T_prefix = c->has_mask ? g.cls_token_num : 0;
       a.scratch = c->at<float>(c->L.attn_scratch);
       a.scratch_bytes = attn_scratch_bytes(c->max_rows, g.n_head, c->D, c->S_max);
+      a.early_prefetch = true;
       rc = !c->force_generic_attn ? launch_attn_tma(g.dtype, a, st) : launch_attn_generic(g.dtype, a, st);
       if (rc) return rc;
       LtLaunch m = t;
@@ -242,6 +243,7 @@ int run_trunk(vlg_ctx* c, const int* pos_ptr, int pos_imm, int max_pos, bool fus
     a.T_prefix = c->has_mask ? g.cls_token_num : 0;
     a.scratch = c->at<float>(c->L.attn_scratch);
     a.scratch_bytes = attn_scratch_bytes(c->max_rows, g.n_head, c->D, c->S_max);
+      a.early_prefetch = true;
     rc = (g.dtype == VLG_BF16 && !c->force_generic_attn) ? launch_attn_tma(g.dtype, a, st) : launch_attn_generic(g.dtype, a, st);
     if (rc) return rc;
     EpiParams Po{};

@@ -78,7 +78,7 @@ __global__ void __launch_bounds__(kAttnTmaThreads, 1)
 attn_decode_tma_kernel(const __grid_constant__ TensorMap tmK, const __grid_constant__ TensorMap tmV,
                        const __nv_bfloat16* __restrict__ q, __nv_bfloat16* __restrict__ out, float* __restrict__ part,
                        int n_rh, int H, int S_max, const int* pos_ptr, int pos_imm,
-                       const uint8_t* __restrict__ mask, int T_prefix, int n_splits) {
+                       const uint8_t* __restrict__ mask, int T_prefix, int n_splits, int early) {
   extern __shared__ uint8_t smem_raw[];
   AttnTmaSmem& sm = *reinterpret_cast<AttnTmaSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -92,7 +92,34 @@ attn_decode_tma_kernel(const __grid_constant__ TensorMap tmK, const __grid_const
   }
   __syncthreads();
   pdl_launch_dependents();
-  pdl_wait();                                // q, the newest K/V row and the position come from the previous kernels
+  // q and the K/V row of the CURRENT position come from the previous kernel; every older cache row was written in earlier
+  // steps.  With `early` the producer starts streaming the first item's old tiles before it waits (the position word was
+  // written by the previous step's sampler, several completed kernels ago -- see launch_attn_tma).
+  uint32_t early_tiles = 0;
+  if (warp == kCW) {
+    if (early && elect_one()) {
+      const int pos_e = pos_ptr ? *pos_ptr : pos_imm;
+      const int n_e = pos_e + 1;
+      int chunk_e = (n_e + n_splits - 1) / n_splits;
+      chunk_e = (chunk_e + kTile - 1) / kTile * kTile;
+      if ((int)blockIdx.x < n_rh * n_splits) {
+        const int rh = blockIdx.x / n_splits, split = blockIdx.x - rh * n_splits;
+        const int s_begin = split * chunk_e, s_end = min(n_e, s_begin + chunk_e);
+        int n_old = s_end > s_begin ? (s_end - s_begin + kTile - 1) / kTile : 0;
+        if (s_end == n_e) n_old -= 1;                    // the tile that holds the current position waits for the predecessor
+        n_old = min(n_old, kStagesA);
+        const int row0 = rh * S_max + s_begin;
+        for (int t = 0; t < n_old; ++t) {
+          mbar_expect_tx(&sm.full[t], kStageBytesA);
+          tma_load_2d_hint(sm.ring[t], &tmK, &sm.full[t], 0, row0 + t * kTile, kEvictFirst);
+          tma_load_2d_hint(sm.ring[t] + kTileBytes, &tmV, &sm.full[t], 0, row0 + t * kTile, kEvictFirst);
+        }
+        early_tiles = n_old > 0 ? (uint32_t)n_old : 0u;
+      }
+    }
+    early_tiles = __reduce_max_sync(0xffffffffu, early_tiles);   // the elected lane's count to the whole warp
+  }
+  pdl_wait();
 
   const int pos = pos_ptr ? *pos_ptr : pos_imm;
   const int n = pos + 1;
@@ -103,13 +130,13 @@ attn_decode_tma_kernel(const __grid_constant__ TensorMap tmK, const __grid_const
   if (warp == kCW) {
     // ------------------------------------------------------------------ TMA producer
     if (elect_one()) {
-      uint32_t gt = 0;
+      uint32_t gt = early_tiles;                          // the first item's leading tiles are already in flight
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         const int rh = item / n_splits, split = item - rh * n_splits;
         const int s_begin = split * chunk, s_end = min(n, s_begin + chunk);
         const int n_tiles = s_end > s_begin ? (s_end - s_begin + kTile - 1) / kTile : 0;
         const int row0 = rh * S_max + s_begin;
-        for (int t = 0; t < n_tiles; ++t, ++gt) {
+        for (int t = item == (int)blockIdx.x ? (int)early_tiles : 0; t < n_tiles; ++t, ++gt) {
           const uint32_t st = gt % kStagesA, it = gt / kStagesA;
           mbar_wait(&sm.empty[st], (it & 1) ^ 1);
           mbar_expect_tx(&sm.full[st], kStageBytesA);
@@ -370,7 +397,7 @@ int launch_attn_tma(int dtype, const AttnArgs& a, cudaStream_t st) {
   const int grid = n_items < sms ? n_items : sms;
   VLG_CUDA(launch_kernel(attn_decode_tma_kernel, dim3(grid), dim3(kAttnTmaThreads), (size_t)smem, st, tmK, tmV,
                          (const __nv_bfloat16*)a.q, (__nv_bfloat16*)a.out, a.scratch, n_rh, a.H, a.S_max, a.pos_ptr,
-                         a.pos_imm, a.prefix_mask, a.T_prefix, n_splits));
+                         a.pos_imm, a.prefix_mask, a.T_prefix, n_splits, a.early_prefetch ? 1 : 0));
   VLG_LAUNCH_CHECK();
   if (n_splits > 1) {
     VLG_CUDA(launch_kernel(attn_tma_combine_kernel, dim3(n_rh), dim3(64), 0, st, (const float*)a.scratch,

@@ -28,6 +28,11 @@ struct AttnArgs {
   float* scratch;       // split partials
   size_t scratch_bytes;
   int max_pos;          // upper bound of pos over the life of a captured graph (sizes the split count)
+  bool early_prefetch;  // TMA kernel only: the producer may read the position and stream old cache rows before
+                        // griddepcontrol.wait.  Safe when everything older than the immediate predecessor has completed by
+                        // the time this kernel's CTAs run -- true in the decode step, where the predecessor (layer-tail or
+                        // QKV GEMM kernel, ~200 KB of shared memory per CTA) cannot share an SM with this kernel, so its CTAs
+                        // have left their own wait long before; false for callers with an unknown predecessor
   int q_per_row;        // generic kernel only, batched prefill: q / out hold q_per_row queries per cache row (positions
                         // pos_imm .. pos_imm + q_per_row - 1); 0 = one query per cache row
 };
