@@ -63,3 +63,6 @@ def test_sass_is_blackwell_native():
     attn = subprocess.run(["cuobjdump", "-sass", os.path.join(ROOT, "video-llamagen_b200", "lib", "attn_tma.o")],
                           capture_output=True, text=True).stdout
     assert "UTMALDG" in attn
+    tail = subprocess.run(["cuobjdump", "-sass", os.path.join(ROOT, "video-llamagen_b200", "lib", "layer_tail.o")],
+                          capture_output=True, text=True).stdout
+    assert "UTCHMMA" in tail and "UTMALDG" in tail and "LDTM" in tail and "HMMA." not in tail.replace("UTCHMMA", "")

@@ -60,3 +60,22 @@ def test_drop_in_import_paths():
     from autoregressive.models.generate import generate, sample, top_k_top_p_filtering  # noqa: F401
     from tokenizer.tokenizer_image.vq_model import VectorQuantizer as V  # noqa: F401
     assert set(G) == {"GPT-B", "GPT-L", "GPT-XL", "GPT-XXL", "GPT-XXXL", "GPT-1B", "GPT-3B", "GPT-7B"}
+    from autoregressive.models.gpt_video import GPT_models as GV
+    from autoregressive.models.generate_video import generate as generate_video   # the module the fork forgot to ship
+    assert set(GV) == set(G) and callable(generate_video)
+
+
+def test_bench_reference_arm_prints_one_contract_line():
+    """`bench.py --impl reference` (the oracle port on the host cores) on a 1-decode-step sample: one JSON line on stdout
+    with the contract's keys, nothing else."""
+    import json, os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                        "--ref-decode-steps", "1"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, r.stdout
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "tokens/s" and d["higher_is_better"] is True and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["e2e"]["h2d_bytes_per_step"] == 0
+    assert d["config"]["workload"].startswith("cfg-2") and d["metric"].startswith("generated visual tokens/sec")
