@@ -143,6 +143,50 @@ def attention_kernel_roofline(dev, rows, H, S_max, n_pos, peak_gbs, src):
             "algorithmic_bytes_per_launch_avg": bytes_total // len(positions)}
 
 
+def layer_tail_roofline(model, dev, rows, new_tokens, peak_gbs, src):
+    """Time the layer-tail kernel alone: the 1 + n_layer launches of one decode position back to back on the real weights
+    (650 MB streamed per replay >> L2), attention skipped (vlg_debug_trunk_without_attention), replayed from a CUDA graph."""
+    import torch
+    from vlg import _lib as L
+    eng = model.engine(rows, 1 + new_tokens)
+    eng.begin(rows)
+    lib = L.lib()
+    st = torch.cuda.Stream(device=dev)
+    cfg = model.config
+    hid = model.layers[0].feed_forward.w1.weight.shape[0]
+    with torch.cuda.stream(st):
+        L.check(lib.vlg_debug_trunk_without_attention(eng.ctx, 100, L.stream()))
+        st.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        reps = 8
+        with torch.cuda.graph(graph, stream=st):
+            for i in range(reps):
+                L.check(lib.vlg_debug_trunk_without_attention(eng.ctx, 100 + i, L.stream()))
+        graph.replay()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        st.synchronize()
+        e0.record(st)
+        graph.replay()
+        e1.record(st)
+        st.synchronize()
+    us = e0.elapsed_time(e1) * 1e3 / (reps * (cfg.n_layer + 1))
+    w_bytes = (4 * cfg.dim * cfg.dim + 3 * cfg.dim * hid) * 2                 # wo + w1|w3 + w2 + wqkv(next layer), bf16
+    act_bytes = rows * (4 * cfg.dim + 2 * hid) * 2                            # attn in, h in/out, xn, ffn, q/k/v out (order of)
+    achieved = (w_bytes + act_bytes) / (us * 1e-6) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r1_lt_ncu_full_step287_metrics.json")
+    if os.path.exists(tpath) and (rows, cfg.dim) == (128, 1024):
+        full = [e for e in json.load(open(tpath)) if "layer_tail" in e["kernel"]][1:]
+        if full:
+            traffic = int(sum(float(e["dram__bytes_read.sum"].split()[0]) + float(e["dram__bytes_write.sum"].split()[0])
+                              for e in full) / len(full) * 1e6)
+    return {"bound": "hbm", "kernel": "layer_tail_kernel", "achieved": round(achieved, 1), "peak": peak_gbs, "unit": "GB/s",
+            "frac": round(achieved / peak_gbs, 4), "traffic": traffic, "peak_source": src, "avg_launch_us": round(us, 2),
+            "launches_timed": reps * (cfg.n_layer + 1), "algorithmic_bytes_per_launch": w_bytes + act_bytes,
+            "note": "one launch per layer for everything between two attentions; streams the layer's weights once, but is "
+                    "bounded by the per-SM L2 port (102 MB L2->SM per launch) and five grid barriers, not by HBM (DESIGN.md 4)"}
+
+
 # --------------------------------------------------------------------------- CPU reference arm (oracle port)
 def cpu_reference_sample(decode_steps, threads=None):
     """Reference algorithm (oracle/ar_decode.py restatement of generate.py + gpt.py) on the host cores: cfg-2 rows and
@@ -305,6 +349,7 @@ def run_vlg(args):
         step_gbs = step_bytes / (ms / args.steps * 1e-3) / 1e9
         roof["whole_step_achieved_gbs"] = round(step_gbs, 1)
         roof["whole_step_frac"] = round(step_gbs / pk["hbm_gbs"], 4)
+        roof2 = layer_tail_roofline(model, dev, 2 * B_LOCAL, NEW_TOKENS, pk["hbm_gbs"], src)
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             cpu, _ = cpu_reference_sample(args.ref_decode_steps)
@@ -314,7 +359,8 @@ def run_vlg(args):
                 "config": workload_config(world), "clocks": clocks,
                 "e2e": {"value": round(tokens_per_step * args.steps / e2e_s, 1), "unit": UNIT,
                         "h2d_bytes_per_step": B_LOCAL * 8 * world, "d2h_bytes_per_step": B_LOCAL * NEW_TOKENS * 4 * world},
-                "gpu_launches": int(launches) * world, "roofline": roof, "cpu_baseline": cpu}
+                "gpu_launches": int(launches) * world, "roofline": roof, "roofline_layer_tail": roof2,
+                "cpu_baseline": cpu}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

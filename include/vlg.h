@@ -223,6 +223,8 @@ size_t vlg_attn_scratch_bytes(int rows, int H, int D, int S_max);
 
 /* instrumentation (VLG_GEMM_DEBUG & 4): globaltimer phase stamps of CTA 0 of the last tcgen05 GEMM; synchronises */
 int vlg_debug_gemm_timestamps(unsigned long long* out16_host);
+/* measurement only: the layer-tail launches of one position (front + one per layer), attention skipped; bf16, rows <= 128 */
+int vlg_debug_trunk_without_attention(vlg_ctx* ctx, int pos, void* stream);
 /* instrumentation (VLG_LT_DEBUG=1): globaltimer phase stamps [160 CTAs][32 slots] of the last full layer-tail launch */
 int vlg_debug_lt_timestamps(unsigned long long* out_host);
 

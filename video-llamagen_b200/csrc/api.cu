@@ -84,6 +84,7 @@ struct vlg_ctx {
   int rows = 0;
   bool has_mask = false;
   bool force_generic_attn = false;   // VLG_ATTN=generic: A/B the two attention kernels
+  bool skip_attention = false;       // measurement only (vlg_debug_trunk_without_attention)
   bool no_fused_norm = true;         // VLG_FUSED_NORM=1 enables the fused RMSNorm prologue of the GEMMs (A/B)
   // graph capture is illegal on the legacy default stream (torch's default): such callers are forked onto this one
   cudaStream_t own_stream = nullptr;
@@ -207,7 +208,7 @@ int run_trunk(vlg_ctx* c, const int* pos_ptr, int pos_imm, int max_pos, bool fus
       a.scratch = c->at<float>(c->L.attn_scratch);
       a.scratch_bytes = attn_scratch_bytes(c->max_rows, g.n_head, c->D, c->S_max);
       a.early_prefetch = true;
-      rc = !c->force_generic_attn ? launch_attn_tma(g.dtype, a, st) : launch_attn_generic(g.dtype, a, st);
+      rc = c->skip_attention ? VLG_OK : (!c->force_generic_attn ? launch_attn_tma(g.dtype, a, st) : launch_attn_generic(g.dtype, a, st));
       if (rc) return rc;
       LtLaunch m = t;
       m.wo = lw.wo; m.w13 = lw.w13; m.w2 = lw.w2; m.norm1_w = lw.ffn_norm;
@@ -775,6 +776,19 @@ extern "C" int vlg_attn_decode(const void* q_dev, const void* k_cache_dev, const
   if (impl == 2) return launch_attn_tma(dtype, a, (cudaStream_t)stream);
   if (impl == 0 && dtype == VLG_BF16) return launch_attn_tma(dtype, a, (cudaStream_t)stream);
   return launch_attn_generic(dtype, a, (cudaStream_t)stream);
+}
+
+// measurement only: the layer-tail launches of one position (front + one per layer) back to back, attention skipped, so that
+// bench.py can time the second-largest kernel alone on the real weights (results are meaningless, buffers are the context's)
+extern "C" int vlg_debug_trunk_without_attention(vlg_ctx* c, int pos, void* stream) {
+  VLG_REQUIRE(c && c->rows > 0, "vlg_debug_trunk_without_attention: call vlg_begin first");
+  VLG_REQUIRE(c->g.dtype == VLG_BF16 && vlg::layer_tail_supported(c->rows, c->g.dim, c->g.hidden_dim),
+              "vlg_debug_trunk_without_attention: the layer-tail kernel does not run for this shape");
+  VLG_REQUIRE(pos >= 0 && pos < c->S_max && pos < c->w.rope_rows, "vlg_debug_trunk_without_attention: pos %d out of range", pos);
+  c->skip_attention = true;
+  const int rc = run_trunk(c, nullptr, pos, pos, false, (cudaStream_t)stream);
+  c->skip_attention = false;
+  return rc;
 }
 
 extern "C" size_t vlg_attn_scratch_bytes(int rows, int H, int D, int S_max) { return attn_scratch_bytes(rows, H, D, S_max); }

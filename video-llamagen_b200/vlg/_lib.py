@@ -64,6 +64,7 @@ SIGNATURES = {
     "vlg_attn_scratch_bytes": (_SZ, [_I, _I, _I, _I]),
     "vlg_debug_gemm_timestamps": (_I, [_P]),
     "vlg_debug_lt_timestamps": (_I, [_P]),
+    "vlg_debug_trunk_without_attention": (_I, [_P, _I, _P]),
 }
 
 _lib = None
