@@ -24,7 +24,18 @@ import sys
 import threading
 import time
 
-os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL's version banner / debug lines go to stderr: stdout carries ONE JSON line
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL's debug lines belong on stderr
+
+# stdout carries ONE JSON line: keep the real stdout for it and point fd 1 at stderr for everything else that might write
+# there from native code (NCCL prints its version banner to fd 1 whenever NCCL_DEBUG is set in the environment).
+_REAL_STDOUT = os.fdopen(os.dup(1), "w")
+sys.stdout.flush()
+os.dup2(2, 1)
+
+
+def emit(line):
+    _REAL_STDOUT.write(json.dumps(line) + "\n")
+    _REAL_STDOUT.flush()
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 for p in (ROOT, os.path.join(ROOT, "video-llamagen_b200")):
@@ -235,7 +246,7 @@ def run_reference(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args.gpus), "cpu_baseline": last,
             "e2e": {"value": round(value, 2), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # --------------------------------------------------------------------------- GPU arm
@@ -311,10 +322,9 @@ def run_vlg(args):
         if args.skip_extras:
             if rank == 0:
                 sampler.stop()
-                print(json.dumps({"metric": METRIC, "value": round(B_LOCAL * NEW_TOKENS * world * args.steps / (ms * 1e-3), 1),
-                                  "unit": UNIT, "ms_per_step": round(ms / args.steps, 2), "new_tokens": NEW_TOKENS,
-                                  "gpu_launches": int(launches), "mode": "profiling run (skip-extras): not a bench value"}),
-                      flush=True)
+                emit({"metric": METRIC, "value": round(B_LOCAL * NEW_TOKENS * world * args.steps / (ms * 1e-3), 1),
+                      "unit": UNIT, "ms_per_step": round(ms / args.steps, 2), "new_tokens": NEW_TOKENS,
+                      "gpu_launches": int(launches), "mode": "profiling run (skip-extras): not a bench value"})
             return
         # e2e: host labels -> host tokens through the C-ABI call (copies + sync inside)
         eng = model._engine
@@ -361,7 +371,7 @@ def run_vlg(args):
                         "h2d_bytes_per_step": B_LOCAL * 8 * world, "d2h_bytes_per_step": B_LOCAL * NEW_TOKENS * 4 * world},
                 "gpu_launches": int(launches) * world, "roofline": roof, "roofline_layer_tail": roof2,
                 "cpu_baseline": cpu}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
