@@ -40,9 +40,14 @@ constexpr int kLtStages = VLG_LT_STAGES;
 constexpr int kLtReaders = (kLtThreads / 32 - 2) >= 8 ? 8 : 4;   // TMEM reader warps: two per lane quadrant when the block has them
 constexpr int kLtHalves = kLtReaders / 4;
 constexpr int kLtABytes = 128 * 64 * 2;    // activation tile: 128 rows x 64 k
-constexpr int kLtStageBytes = 2 * kLtABytes;   // + weight tile of up to 128 rows x 64 k
+// Ring layouts (template parameters of the kernel): a stage = activation tile + weight tile slot.  Shapes whose column tiles
+// are all <= 64 wide use 24 KB stages and a 9-deep ring, the others 32 KB stages and 6: the ingest-bound phases want as
+// many bytes in flight as shared memory holds (4 / 5 / 6 stages of 32 KB: 831 / 809 / 800 ms per cfg-2 generate).
+constexpr int kLtStageBytesWide = 2 * kLtABytes;          // weight tile of up to 128 rows x 64 k
+constexpr int kLtStageBytesNarrow = kLtABytes + 8192;     // weight tile of up to 64 rows x 64 k
+constexpr int kLtStagesNarrow = 9;
 constexpr int kLtTmemCols = 128;
-constexpr int kLtSmemBytes = kLtStages * kLtStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int lt_smem_bytes(int stages, int stage_bytes) { return stages * stage_bytes + 1024 /*align slack*/ + 512 /*barriers*/; }
 
 struct LtGemm {
   int N, K;        // out features, in features
@@ -136,8 +141,8 @@ __device__ __forceinline__ void lt_grid_barrier(unsigned* ctr, unsigned& target)
   tc_fence_after();
 }
 
-struct LtSmem {
-  uint64_t full[kLtStages], empty[kLtStages];
+template <int ST> struct LtSmem {
+  uint64_t full[ST], empty[ST];
   uint64_t acc_ready;
   uint32_t tmem_slot;
   float red[kLtThreads / 32];
@@ -146,25 +151,26 @@ struct LtSmem {
 // ---------------------------------------------------------------------------------------------------- GEMM phase
 // g: k-blocks this CTA has pushed through the ring so far (producer and MMA issuer walk the same sequence);
 // acc_uses: GEMM phases in which this CTA owned a unit (parity of acc_ready).
-__device__ __forceinline__ void lt_prefetch_b(const LtGemm& G, const TensorMap* tmB, uint8_t* ring, LtSmem& sm, uint32_t g) {
+template <int ST, int SB>
+__device__ __forceinline__ void lt_prefetch_b(const LtGemm& G, const TensorMap* tmB, uint8_t* ring, LtSmem<ST>& sm, uint32_t g) {
   const LtUnit v = lt_unit(G, blockIdx.x);
   if (!v.valid) return;
-  const int pre = v.nkb < kLtStages ? v.nkb : kLtStages;
+  const int pre = v.nkb < ST ? v.nkb : ST;
   const uint32_t tx = kLtABytes + G.BN * 128;
   for (int kb = 0; kb < pre; ++kb) {
-    const uint32_t s = (g + kb) % kLtStages, it = (g + kb) / kLtStages;
+    const uint32_t s = (g + kb) % ST, it = (g + kb) / ST;
     mbar_wait(&sm.empty[s], (it & 1) ^ 1);
     mbar_expect_tx(&sm.full[s], tx);
-    tma_load_2d_hint(ring + s * kLtStageBytes + kLtABytes, tmB, &sm.full[s], (v.kb0 + kb) * 64, v.n0, kEvictFirst);
+    tma_load_2d_hint(ring + s * SB + kLtABytes, tmB, &sm.full[s], (v.kb0 + kb) * 64, v.n0, kEvictFirst);
   }
 }
 
 // MODE: -1 = store the fp32 partial tile (split-K, reduced by the following row phase); EPI_SWIGLU / EPI_QKV_ROPE = the unit
 // owns all of K and applies the elementwise tail straight from TMEM (lane == row).
-template <int MODE>
+template <int MODE, int ST, int SB>
 __device__ __forceinline__ void lt_gemm_phase(const LtGemm& G, const TensorMap* tmA, const TensorMap* tmB,
                                               const LtGemm* Gnext, const TensorMap* tmBnext, const LtParams& P,
-                                              const EpiParams& E, uint8_t* ring, LtSmem& sm, uint32_t tmem_acc, uint32_t& g, uint32_t& acc_uses,
+                                              const EpiParams& E, uint8_t* ring, LtSmem<ST>& sm, uint32_t tmem_acc, uint32_t& g, uint32_t& acc_uses,
                                               int ts_slot) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const LtUnit u = lt_unit(G, blockIdx.x);
@@ -173,32 +179,32 @@ __device__ __forceinline__ void lt_gemm_phase(const LtGemm& G, const TensorMap* 
     if (elect_one()) {
       asm volatile("fence.proxy.async;" ::: "memory");     // other SMs' generic-proxy stores of A -> this SM's TMA reads
       if (u.valid) {
-        const int pre = u.nkb < kLtStages ? u.nkb : kLtStages;      // their weight tiles + expect_tx were issued a phase ago
+        const int pre = u.nkb < ST ? u.nkb : ST;      // their weight tiles + expect_tx were issued a phase ago
         for (int kb = 0; kb < pre; ++kb) {
-          const uint32_t s = (g + kb) % kLtStages;
-          tma_load_2d_hint(ring + s * kLtStageBytes, tmA, &sm.full[s], (u.kb0 + kb) * 64, 0, kEvictLast);
+          const uint32_t s = (g + kb) % ST;
+          tma_load_2d_hint(ring + s * SB, tmA, &sm.full[s], (u.kb0 + kb) * 64, 0, kEvictLast);
         }
         const uint32_t tx = kLtABytes + G.BN * 128;
         for (int kb = pre; kb < u.nkb; ++kb) {
-          const uint32_t s = (g + kb) % kLtStages, it = (g + kb) / kLtStages;
+          const uint32_t s = (g + kb) % ST, it = (g + kb) / ST;
           mbar_wait(&sm.empty[s], (it & 1) ^ 1);
           mbar_expect_tx(&sm.full[s], tx);
-          uint8_t* a = ring + s * kLtStageBytes;
+          uint8_t* a = ring + s * SB;
           tma_load_2d_hint(a, tmA, &sm.full[s], (u.kb0 + kb) * 64, 0, kEvictLast);
           tma_load_2d_hint(a + kLtABytes, tmB, &sm.full[s], (u.kb0 + kb) * 64, u.n0, kEvictFirst);
         }
       }
-      if (Gnext != nullptr) lt_prefetch_b(*Gnext, tmBnext, ring, sm, g + nkb);
+      if (Gnext != nullptr) lt_prefetch_b<ST, SB>(*Gnext, tmBnext, ring, sm, g + nkb);
     }
     __syncwarp();
   } else if (warp == 1) {
     if (u.valid && elect_one()) {
       const uint32_t idesc = umma_idesc_bf16(128, G.BN);
       for (int kb = 0; kb < u.nkb; ++kb) {
-        const uint32_t s = (g + kb) % kLtStages, it = (g + kb) / kLtStages;
+        const uint32_t s = (g + kb) % ST, it = (g + kb) / ST;
         mbar_wait(&sm.full[s], it & 1);
         tc_fence_after();
-        const uint32_t a_addr = smem_u32(ring + s * kLtStageBytes);
+        const uint32_t a_addr = smem_u32(ring + s * SB);
         const uint64_t adesc = umma_desc_sw128(a_addr), bdesc = umma_desc_sw128(a_addr + kLtABytes);
 #pragma unroll
         for (int k = 0; k < 4; ++k) umma_bf16(tmem_acc, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
@@ -306,7 +312,8 @@ __device__ __forceinline__ void lt_reduce8(const float* part, int S, size_t spli
 }
 
 // h <- T(h + T(sum of partials))  (when G != null), then xn <- T(T(h * rsqrt(mean(h^2) + eps)) * w): one row per CTA
-__device__ __forceinline__ void lt_norm_phase(const LtGemm* G, const __nv_bfloat16* w, const LtParams& P, LtSmem& sm) {
+template <int ST>
+__device__ __forceinline__ void lt_norm_phase(const LtGemm* G, const __nv_bfloat16* w, const LtParams& P, LtSmem<ST>& sm) {
   const int nvec = P.dim / 8, t = threadIdx.x;
   const bool active = t < nvec;
   float g8[8];
@@ -347,6 +354,7 @@ __device__ __forceinline__ void lt_norm_phase(const LtGemm* G, const __nv_bfloat
 }
 
 // ---------------------------------------------------------------------------------------------------- the kernel
+template <int ST, int SB>
 __global__ void __launch_bounds__(kLtThreads, 1)
 layer_tail_kernel(const __grid_constant__ TensorMap tmAttn, const __grid_constant__ TensorMap tmXn,
                   const __grid_constant__ TensorMap tmFfn, const __grid_constant__ TensorMap tmWo,
@@ -354,14 +362,14 @@ layer_tail_kernel(const __grid_constant__ TensorMap tmAttn, const __grid_constan
                   const __grid_constant__ TensorMap tmWqkv, const LtParams P) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  LtSmem& sm = *reinterpret_cast<LtSmem*>(ring + kLtStages * kLtStageBytes);
+  LtSmem<ST>& sm = *reinterpret_cast<LtSmem<ST>*>(ring + ST * SB);
   const int warp = threadIdx.x >> 5;
 
   if (threadIdx.x == 0) {
     if (P.has_front) { tma_prefetch_desc(&tmAttn); tma_prefetch_desc(&tmFfn); tma_prefetch_desc(&tmWo); tma_prefetch_desc(&tmW13); tma_prefetch_desc(&tmW2); }
     tma_prefetch_desc(&tmXn);
     if (P.has_qkv) tma_prefetch_desc(&tmWqkv);
-    for (int s = 0; s < kLtStages; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], 1); }
+    for (int s = 0; s < ST; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], 1); }
     mbar_init(&sm.acc_ready, 1);
     fence_mbar_init();
   }
@@ -378,8 +386,8 @@ layer_tail_kernel(const __grid_constant__ TensorMap tmAttn, const __grid_constan
   // the first GEMM's weight tiles do not depend on the previous kernel: request them before waiting for it
   if (warp == 0) {
     if (elect_one()) {
-      if (P.has_front) lt_prefetch_b(P.g_wo, &tmWo, ring, sm, 0);
-      else if (P.has_qkv) lt_prefetch_b(P.g_qkv, &tmWqkv, ring, sm, 0);
+      if (P.has_front) lt_prefetch_b<ST, SB>(P.g_wo, &tmWo, ring, sm, 0);
+      else if (P.has_qkv) lt_prefetch_b<ST, SB>(P.g_qkv, &tmWqkv, ring, sm, 0);
     }
     __syncwarp();
   }
@@ -387,7 +395,7 @@ layer_tail_kernel(const __grid_constant__ TensorMap tmAttn, const __grid_constan
   LT_TS(1);
 
   if (P.has_front) {
-    lt_gemm_phase<-1>(P.g_wo, &tmAttn, &tmWo, &P.g_w13, &tmW13, P, P.ffn, ring, sm, tmem_acc, g, acc_uses, 16);
+    lt_gemm_phase<-1, ST, SB>(P.g_wo, &tmAttn, &tmWo, &P.g_w13, &tmW13, P, P.ffn, ring, sm, tmem_acc, g, acc_uses, 16);
     LT_TS(2);
     lt_grid_barrier(P.bar, bar_target);
     LT_TS(3);
@@ -395,11 +403,11 @@ layer_tail_kernel(const __grid_constant__ TensorMap tmAttn, const __grid_constan
     LT_TS(4);
     lt_grid_barrier(P.bar, bar_target);
     LT_TS(5);
-    lt_gemm_phase<EPI_SWIGLU>(P.g_w13, &tmXn, &tmW13, &P.g_w2, &tmW2, P, P.ffn, ring, sm, tmem_acc, g, acc_uses, 18);
+    lt_gemm_phase<EPI_SWIGLU, ST, SB>(P.g_w13, &tmXn, &tmW13, &P.g_w2, &tmW2, P, P.ffn, ring, sm, tmem_acc, g, acc_uses, 18);
     LT_TS(6);
     lt_grid_barrier(P.bar, bar_target);
     LT_TS(7);
-    lt_gemm_phase<-1>(P.g_w2, &tmFfn, &tmW2, P.has_qkv ? &P.g_qkv : nullptr, &tmWqkv, P, P.ffn, ring, sm, tmem_acc, g, acc_uses, 20);
+    lt_gemm_phase<-1, ST, SB>(P.g_w2, &tmFfn, &tmW2, P.has_qkv ? &P.g_qkv : nullptr, &tmWqkv, P, P.ffn, ring, sm, tmem_acc, g, acc_uses, 20);
     LT_TS(8);
     lt_grid_barrier(P.bar, bar_target);
     LT_TS(9);
@@ -411,7 +419,7 @@ layer_tail_kernel(const __grid_constant__ TensorMap tmAttn, const __grid_constan
   if (P.has_qkv) {
     lt_grid_barrier(P.bar, bar_target);
     LT_TS(11);
-    lt_gemm_phase<EPI_QKV_ROPE>(P.g_qkv, &tmXn, &tmWqkv, nullptr, nullptr, P, P.rope, ring, sm, tmem_acc, g, acc_uses, 22);
+    lt_gemm_phase<EPI_QKV_ROPE, ST, SB>(P.g_qkv, &tmXn, &tmWqkv, nullptr, nullptr, P, P.rope, ring, sm, tmem_acc, g, acc_uses, 22);
     LT_TS(12);
   }
 
@@ -524,13 +532,16 @@ int launch_layer_tail(const LtLaunch& a, cudaStream_t st) {
   if (P.has_qkv)
     if ((rc = make_tmap_bf16_2d(&tmWqkv, a.wqkv, (uint64_t)3 * a.dim, (uint64_t)a.dim, (uint64_t)a.dim * 2, P.g_qkv.BN, 64, true))) return rc;
 
-  static bool attr_set = false;
-  if (!attr_set) {
-    VLG_CUDA(cudaFuncSetAttribute(layer_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kLtSmemBytes));
-    attr_set = true;
+  // ring layout by the widest column tile in use (see kLtStagesNarrow)
+  const bool narrow = P.g_wo.BN <= 64 && P.g_w13.BN <= 64 && P.g_w2.BN <= 64 && P.g_qkv.BN <= 64;
+  auto kern = narrow ? layer_tail_kernel<kLtStagesNarrow, kLtStageBytesNarrow> : layer_tail_kernel<kLtStages, kLtStageBytesWide>;
+  const int smem = narrow ? lt_smem_bytes(kLtStagesNarrow, kLtStageBytesNarrow) : lt_smem_bytes(kLtStages, kLtStageBytesWide);
+  static bool attr_set[2] = {false, false};
+  if (!attr_set[narrow]) {
+    VLG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set[narrow] = true;
   }
-  VLG_CUDA(launch_kernel(layer_tail_kernel, dim3(sms), dim3(kLtThreads), (size_t)kLtSmemBytes, st, tmAttn, tmXn, tmFfn, tmWo,
-                         tmW13, tmW2, tmWqkv, P));
+  VLG_CUDA(launch_kernel(kern, dim3(sms), dim3(kLtThreads), (size_t)smem, st, tmAttn, tmXn, tmFfn, tmWo, tmW13, tmW2, tmWqkv, P));
   VLG_LAUNCH_CHECK();
   return VLG_OK;
 }
