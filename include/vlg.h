@@ -54,13 +54,23 @@ const char* vlg_last_error(void);
  * codebook_dev fp32 [n_e, C]    raw embedding.weight (normalised inside when l2_norm != 0)
  * idx_dev      int64 [B*HW]     argmin_j ( |z|^2 + |e_j|^2 - 2 z.e_j ), first index on ties
  * zq_dev       fp32 [B, C, HW]  selected (normalised) codebook rows, channel-first; may be NULL
- * scratch_dev  fp32 [n_e * (C+1)] work area for the normalised codebook and |e_j|^2          */
+ * scratch_dev  fp32 [vlg_vq_scratch_floats(B*HW, C, n_e)] work area: normalised codebook, |e_j|^2 and the list of
+ *              latents whose two best codes are closer than fp32 rounding (settled by an exact second pass) */
+size_t vlg_vq_scratch_floats(int64_t N, int C, int n_e);
 int vlg_vq_argmin(const float* z_dev, const float* codebook_dev, int64_t* idx_dev, float* zq_dev,
                   float* scratch_dev, int64_t B, int C, int64_t HW, int n_e, int l2_norm, void* stream);
 
 /* out_dev fp32: channel_first ? [B, C, HW] : [B*HW, C]  = normalise(codebook)[idx] */
 int vlg_codebook_gather(const int64_t* idx_dev, const float* codebook_dev, float* out_dev, int64_t B, int C,
                         int64_t HW, int n_e, int l2_norm, int channel_first, void* stream);
+
+/* First step of VQModel.decode_code (vq_model.py:53-55 -> :47-48): get_codebook_entry fused with the 1x1
+ * post_quant_conv, so the [B, C, HW] quantised map is never written.
+ * out_dev fp32 [B, O, HW] = bias[o] + sum_c weight[o, c] * normalise(codebook)[idx[b*HW + hw], c]
+ * weight_dev fp32 [O, C] (post_quant_conv.weight viewed 2-D), bias_dev fp32 [O] or NULL.          */
+int vlg_codebook_project(const int64_t* idx_dev, const float* codebook_dev, const float* weight_dev,
+                         const float* bias_dev, float* out_dev, int64_t B, int C, int64_t HW, int n_e, int O,
+                         int l2_norm, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Sampling -- replaces decode_one_token's CFG mix (generate.py:95-99), top_k_top_p_filtering
@@ -190,6 +200,16 @@ int vlg_generate(vlg_ctx* ctx, const vlg_generate_params* p, const void* cond_de
  * vae_latent_adapter2.fc2 to 16 output rows by the caller (tensor-core tile granularity). */
 int vlg_generate_t2v(vlg_ctx* ctx, const vlg_generate_params* p, const void* cond_dev, const void* uncond_dev,
                      const uint8_t* emb_masks_dev, void* latents_dev, void* stream);
+
+/* Measurement only: register-resident FP32 FMA loop on every SM (variant 0: FFMA, 1: packed FFMA2); the caller times
+ * it with events.  *flops_out = floating-point operations of the launch.  The roofline denominator of vlg_vq_argmin. */
+int vlg_debug_fp32_fma_peak(int variant, int iters, float* out_dev, long long* flops_out, void* stream);
+
+/* Synchronises `stream` and reports whether any layer-tail launch of this context since the last check gave up in its
+ * grid barrier (VLG_ERR_STATE: its CTAs were not co-resident because other work occupied SMs of the GPU; the outputs are
+ * invalid and the call should be repeated once the GPU is free).  Every other context call performs the same check,
+ * without synchronising, on entry; vlg_generate_c2i_host also on exit. */
+int vlg_ctx_check(vlg_ctx* ctx, void* stream);
 
 /* Same with HOST buffers (pinned or pageable): copies cond in, runs, copies tokens out and synchronises
  * the stream.  This is the call the end-to-end benchmark times. c2i only (labels int64 [B]). */

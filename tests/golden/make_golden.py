@@ -223,23 +223,52 @@ def vq(ref):
 
 
 def gptb(ref):
-    """cfg-1 geometry (GPT-B c2i 256 px, CFG 4.0) at reduced length: weights are NOT
-    stored; they are re-created from the seed by the product's own constructor, whose
-    parameter-creation order must therefore match the reference's (checksums below)."""
+    """BASELINE cfg-1 at its stated size: GPT-B c2i 256 px (16x16 = 256 tokens), batch 4, CFG 4.0, fp32, the reference on
+    CPU -- greedy (top-k 1) so that the token sequences are the bit-exact contract.  Weights are NOT stored; they are
+    re-created from the seed by the product's own constructor, whose parameter-creation order must therefore match the
+    reference's (checksums below).  `gap` is the oracle's top-1 / top-2 distance of the CFG-mixed fp32 logits at every
+    step of that sequence: the diagnostic to print when a kernel diverges (hard part 1)."""
+    from oracle import ar_decode as O
     torch.manual_seed(0)
     model = ref.gpt.GPT_models["GPT-B"](block_size=256, cls_token_num=1, model_type="c2i").eval()
     torch.nn.init.normal_(model.output.weight, std=0.02)
-    sums = {k: np.array([float(v.double().sum()), float(v.double().abs().sum())])
-            for k, v in model.state_dict().items() if "kv_cache" not in k}
-    cond = torch.tensor([17, 980])
-    greedy = ref.generate.generate(model, cond, 24, cfg_scale=4.0, temperature=1.0, top_k=1, top_p=1.0,
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items() if "kv_cache" not in k}
+    sums = {k: np.array([float(v.double().sum()), float(v.double().abs().sum())]) for k, v in sd.items()}
+    cond = torch.randint(0, 1000, (4,), generator=torch.Generator().manual_seed(1234))
+    greedy = ref.generate.generate(model, cond, 256, cfg_scale=4.0, temperature=1.0, top_k=1, top_p=1.0,
                                    sample_logits=False)
-    save("gptb_greedy.npz", cond=cond.numpy(), greedy=greedy.numpy(), **{"sum." + k: v for k, v in sums.items()})
+    geo = O.Geometry(block_size=256, **O.NAMED["GPT-B"])
+    logits = O.teacher_forced_logits(geo, sd, cond, greedy[:, :-1].long())          # [N, 2B, V] raw
+    mixed = torch.stack([O.cfg_mix(l.unsqueeze(1), 4.0)[:, 0] for l in logits])      # [N, B, V]
+    top2 = mixed.topk(2, dim=-1)
+    assert torch.equal(top2.indices[..., 0].t().int(), greedy), "oracle and reference disagree on the greedy sequence"
+    gap = (top2.values[..., 0] - top2.values[..., 1]).t().contiguous()               # [B, N]
+    save("gptb_greedy.npz", cond=cond.numpy(), greedy=greedy.numpy(), gap=gap.numpy(),
+         **{"sum." + k: v for k, v in sums.items()})
+
+
+def vqmodel(ref):
+    """VQ-16 tokenizer (vq_model.py:28-62): encode() of a seeded image and decode_code() of seeded codes through the
+    reference module on CPU fp32.  Weights are re-created from the seed (72 M parameters are not stored): checksums pin
+    the construction order."""
+    torch.manual_seed(0)
+    m = ref.vq_model.VQ_models["VQ-16"](codebook_size=16384, codebook_embed_dim=8).eval()
+    sums = {k: np.array([float(v.double().sum()), float(v.double().abs().sum())]) for k, v in m.state_dict().items()}
+    g = torch.Generator().manual_seed(4321)
+    x = torch.randn(2, 3, 64, 64, generator=g)
+    with torch.no_grad():
+        h = m.quant_conv(m.encoder(x))
+        quant, _, (_, _, idx) = m.encode(x)
+        codes = torch.randint(0, 16384, (2 * 8 * 8,), generator=g)
+        img = m.decode_code(codes, (2, 8, 8, 8))
+        feat = m.post_quant_conv(m.quantize.get_codebook_entry(codes, (2, 8, 8, 8)))
+    save("vqmodel.npz", x=x.numpy(), h=h.numpy(), quant=quant.numpy(), idx=idx.numpy(), codes=codes.numpy(),
+         img=img.numpy(), feat=feat.numpy(), **{"sum." + k: v for k, v in sums.items()})
 
 
 if __name__ == "__main__":
     ref = _reference.load()
-    which = sys.argv[1:] or ["c2i", "t2i", "t2v", "sampling", "vq", "gptb"]
+    which = sys.argv[1:] or ["c2i", "t2i", "t2v", "sampling", "vq", "gptb", "vqmodel"]
     with torch.no_grad():
         if "c2i" in which:
             c2i_tiny(ref)
@@ -251,6 +280,8 @@ if __name__ == "__main__":
             vq(ref)
         if "gptb" in which:
             gptb(ref)
+        if "vqmodel" in which:
+            vqmodel(ref)
         if "t2v" in which:
             t2v_tiny(_reference.load(video=True))
         if "t2vgen" in which:

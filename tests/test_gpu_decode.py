@@ -114,15 +114,23 @@ def test_c2i_tiny_bf16_logits_within_tolerance(golden):
 
 
 def test_gptb_fp32_greedy_matches_reference(golden):
-    """cfg-1 geometry (GPT-B c2i 256 px, CFG 4.0), weights recreated from the seed by the drop-in constructor."""
+    """BASELINE cfg-1 at its stated size (GPT-B c2i 256 px, batch 4, CFG 4.0, all 256 tokens), fp32 greedy: bit-exact
+    against the sequence the reference produced on CPU; weights recreated from the seed by the drop-in constructor.
+    On a divergence the message names the first mismatching step and the oracle's top-2 logit gap there (a gap at fp32
+    rounding level would mean a legitimate summation-order flip, anything larger a kernel bug)."""
     f = golden("gptb_greedy.npz")
     torch.manual_seed(0)
     m = GPT_models["GPT-B"](block_size=256, cls_token_num=1, model_type="c2i").eval()
     torch.nn.init.normal_(m.output.weight, std=0.02)
     m = m.to(DEV)
     cond = torch.from_numpy(f["cond"]).to(DEV)
-    g = generate(m, cond, 24, cfg_scale=4.0, temperature=1.0, top_k=1, top_p=1.0, sample_logits=False)
-    assert np.array_equal(g.cpu().numpy(), f["greedy"])
+    assert f["greedy"].shape == (4, 256)
+    g = generate(m, cond, 256, cfg_scale=4.0, temperature=1.0, top_k=1, top_p=1.0, sample_logits=False).cpu().numpy()
+    if not np.array_equal(g, f["greedy"]):
+        bad = np.argwhere(g != f["greedy"])
+        b, i = min(map(tuple, bad), key=lambda t: t[1])
+        raise AssertionError(f"first mismatch: sample {b} step {i}: got {g[b, i]} want {f['greedy'][b, i]}; oracle top-2 "
+                             f"gap there {f['gap'][b, i]:.3e} (min gap over the run {f['gap'].min():.3e})")
 
 
 def test_gptl_cfg2_full_size_bf16():
@@ -186,6 +194,36 @@ def test_layer_tail_geometries_bf16(name, n_layer, B):
     assert rms_ours <= 1.5 * rms_ref + 1e-4, (rms_ours, rms_ref)
 
 
+def test_gptxxl_cfg3_full_depth_shard_bf16():
+    """BASELINE cfg-3, one rank's shard at full size: GPT-XXL (48 layers, d = 1536, 24 heads, hidden 4096), 32 samples with
+    CFG = 64 cache rows, V = 16384, 576-token caches; prefill + 8 teacher-forced decode steps, raw bf16 logits against the
+    reference algorithm in bf16 on this GPU, and no noisier than it against the same weights in fp32 math."""
+    geo = O.Geometry(block_size=576, **O.NAMED["GPT-XXL"])
+    w = O.init_weights(geo, seed=1, dtype=torch.float32, embed_std=0.3)
+    m = GPT_models["GPT-XXL"](block_size=576, cls_token_num=1, model_type="c2i").eval()
+    m.load_state_dict(w, strict=True)
+    m = m.to(DEV, torch.bfloat16)
+    g = torch.Generator().manual_seed(1234)
+    cond = torch.randint(0, 1000, (32,), generator=g).to(DEV)
+    toks = torch.randint(0, 16384, (32, 8), generator=g).to(DEV)
+    w16 = {k: v.to(DEV, torch.bfloat16) for k, v in w.items()}
+    del w
+    ref = O.teacher_forced_logits(geo, w16, cond, toks)
+    truth = O.teacher_forced_logits(geo, {k: v.float() for k, v in w16.items()}, cond, toks)
+    rows = torch.cat([cond, torch.ones_like(cond) * 1000])
+    m.setup_caches(64, 1 + 576, None)                      # the caches of the full 576-token run
+    out = [m(None, rows, torch.arange(1, device=DEV))[0][:, -1]]
+    for i in range(toks.shape[1]):
+        x = torch.cat([toks[:, i:i + 1], toks[:, i:i + 1]])
+        out.append(m(x, None, torch.tensor([1 + i], device=DEV))[0][:, -1])
+    ours = torch.stack(out).float()
+    scale = max(1.0, truth.pow(2).mean().sqrt().item() / 0.55)
+    assert torch.allclose(ours, ref, rtol=BF16_RTOL, atol=BF16_ATOL * scale), ((ours - ref).abs().max(), scale)
+    rms_ours = (ours - truth).pow(2).mean().sqrt().item()
+    rms_ref = (ref - truth).pow(2).mean().sqrt().item()
+    assert rms_ours <= 1.5 * rms_ref + 1e-4, (rms_ours, rms_ref)
+
+
 def test_t2v_tiny_trunk_adapters_3d_rope(golden):
     """BASELINE cfg-4 path at fixture size: 120-token masked caption prefix, CFG row doubling, latent adapters in/out,
     3D RoPE table, continuous-latent output (gpt_video.py:403-431) -- fp32 against the reference fixture, then bf16
@@ -219,9 +257,23 @@ def test_t2v_tiny_trunk_adapters_3d_rope(golden):
     assert np.abs(o32.cpu().numpy() - f["out"]).max() < 1e-4
     if f["w.cls_embedding.cap_proj.fc1.weight"].shape[1] % 64 == 0:
         o16 = run(m, torch.bfloat16)
-        # bf16 end to end (weights, activations, cache) vs fp32: relative to the latent scale (|o| ~ 10 in this fixture)
-        assert (o16 - o32).abs().max() < 0.03 * o32.abs().max()
-        assert (o16 - o32).pow(2).mean().sqrt() < 0.01 * o32.pow(2).mean().sqrt()
+        # bf16 end to end (weights, activations, cache; zero-padded adapter ends on the tensor cores) against the reference
+        # algorithm in bf16 on this GPU, teacher-forced on the same latents; `truth` is the fp32 reference fixture
+        w16 = weights_from(f, torch.bfloat16, DEV)
+        st = O.DecodeState(TINY_T2V, 4, T + N, torch.bfloat16, DEV)
+        st.apply_prefix_mask(torch.cat([masks, masks]).to(DEV))
+        rows16 = torch.cat([cond, torch.zeros_like(cond) + f["w.cls_embedding.uncond_embedding"]]).to(DEV, torch.bfloat16)
+        ref = [O.forward_latent(TINY_T2V, w16, st, cond=rows16, input_pos=torch.arange(T, device=DEV))[:, -1]]
+        for i in range(N - 1):
+            x = torch.cat([lat[:, i:i + 1], lat[:, i:i + 1]]).to(DEV, torch.bfloat16)
+            ref.append(O.forward_latent(TINY_T2V, w16, st, latent=x, input_pos=torch.tensor([T + i], device=DEV))[:, -1])
+        ref = torch.stack(ref).float()
+        truth = torch.from_numpy(f["out"]).to(DEV)
+        scale = max(1.0, truth.pow(2).mean().sqrt().item() / 0.55)
+        assert torch.allclose(o16, ref, rtol=BF16_RTOL, atol=BF16_ATOL * scale), ((o16 - ref).abs().max(), scale)
+        rms_ours = (o16 - truth).pow(2).mean().sqrt().item()
+        rms_ref = (ref - truth).pow(2).mean().sqrt().item()
+        assert rms_ours <= 1.5 * rms_ref + 1e-4, (rms_ours, rms_ref)
 
 
 def test_t2v_generate_loop(golden):
@@ -257,11 +309,16 @@ def test_t2v_generate_loop(golden):
     if f["w.cls_embedding.cap_proj.fc1.weight"].shape[1] % 64 == 0:
         m16 = m.to(DEV, torch.bfloat16)
         o16 = generate_video(m16, cond.to(DEV), N, masks.to(DEV), cfg_scale=4.0).float()
-        o32 = torch.from_numpy(gold["gen"]).to(DEV)
-        # bf16 end to end with the latent fed back through a chaotic map: the first latent (prefill) must agree, the rest
-        # must stay finite and on the fp32 run's scale
-        assert (o16[:, 0] - o32[:, 0]).abs().max() < 0.03 * o32[:, 0].abs().max()
-        assert torch.isfinite(o16).all() and o16.abs().max() < 2 * o32.abs().max()
+        # bf16 loop against the reference algorithm's bf16 loop on this GPU (O.generate_video).  The latent is fed back
+        # through a chaotic map (rounding noise grows ~1.6x per step, see the oracle's own test), so the standard bf16 gate
+        # applies to the first latent and doubles with every further step; the whole run must stay on the oracle's scale.
+        ref16 = O.generate_video(TINY_T2V, weights_from(f, torch.bfloat16, DEV), cond.to(DEV, torch.bfloat16), N,
+                                 masks.to(DEV), cfg_scale=4.0).float()
+        scale = max(1.0, ref16.pow(2).mean().sqrt().item() / 0.55)
+        for k in range(4):
+            tol = BF16_ATOL * scale * 2 ** k + BF16_RTOL * 2 ** k * ref16[:, k].abs()
+            assert bool(((o16[:, k] - ref16[:, k]).abs() <= tol).all()), (k, (o16[:, k] - ref16[:, k]).abs().max())
+        assert torch.isfinite(o16).all() and o16.abs().max() < 2 * ref16.abs().max()
 
 
 def test_batched_prefill_equals_stepped_prefill(golden):
@@ -290,3 +347,45 @@ def test_batched_prefill_equals_stepped_prefill(golden):
         outs.append(json.loads(r.stdout.strip().splitlines()[-1]))
     assert outs[0] == outs[1]
     assert np.array_equal(np.array(outs[0]), golden("t2i_tiny.npz")["greedy"])
+
+
+def test_generate_loop_tokens_follow_the_distribution():
+    """The graph-replayed loop on a model whose logits cannot depend on the input (all embedding rows identical, so every
+    K/V row is the same and attention returns it whatever the softmax weights are): the 8 x 2025 tokens vlg_generate
+    emits are then iid draws from softmax(top-k(logits)) -- chi-square against that distribution, plus the step-to-step
+    independence of the Philox stream (offset = step)."""
+    torch.manual_seed(2)
+    V, N, B = 64, 2025, 8
+    m = Transformer(ModelArgs(dim=128, n_layer=2, n_head=2, vocab_size=V, block_size=N, multiple_of=64, cls_token_num=1,
+                              num_classes=10, model_type="c2i")).eval()
+    torch.nn.init.normal_(m.output.weight, std=0.4)
+    with torch.no_grad():
+        row = torch.randn(128) * 0.5
+        m.tok_embeddings.weight.copy_(row.expand_as(m.tok_embeddings.weight))
+        m.cls_embedding.embedding_table.weight.copy_(row.expand_as(m.cls_embedding.embedding_table.weight))
+    m = m.to(DEV, torch.bfloat16)
+    cond = torch.arange(B, device=DEV) % 10
+    # the distribution the loop draws from, through the step API of the same model (prefill logits == every step's logits
+    # up to the last-bit wobble of sum(p_j v) / sum(p_j) over a growing prefix)
+    rows = torch.cat([cond, torch.ones_like(cond) * 10])
+    m.setup_caches(2 * B, 1 + 8, None)
+    l0 = m(None, rows, torch.arange(1, device=DEV))[0][:, -1]
+    l1 = m(torch.full((2 * B, 1), 3, device=DEV), None, torch.tensor([1], device=DEV))[0][:, -1]
+    assert (l0 - l1).abs().max() < 0.05 and (l0 - l0[:1]).abs().max() < 0.05, "the fixed-logit construction leaked the input"
+    srt = l0[0].float().sort(descending=True).values
+    k = 10 + int((srt[9:30] - srt[10:31]).argmax())                    # top-k cut at the widest gap: no threshold flips
+    toks = generate(m, cond, N, cfg_scale=4.0, temperature=1.0, top_k=k, top_p=1.0, sample_logits=True, seed=5)
+    _, p = sample(l0[:1].unsqueeze(1).float(), temperature=1.0, top_k=k, sample_logits=False)
+    p = p[0].cpu()
+    n = B * N
+    freq = torch.bincount(toks.flatten().cpu().long(), minlength=V).double()
+    assert int(freq[p == 0].sum()) == 0
+    e = p[p > 0].double() * n
+    chi2 = float((((freq[p > 0] - e) ** 2) / e).sum())
+    dof = int((p > 0).sum()) - 1
+    assert chi2 < dof + 8 * (2 * dof) ** 0.5, (chi2, dof)
+    same = float(p.pow(2).sum())
+    t = toks.cpu()
+    for frac, cnt in ((float((t[:, 1:] == t[:, :-1]).float().mean()), B * (N - 1)),       # consecutive steps
+                      (float((t[1:] == t[:-1]).float().mean()), (B - 1) * N)):            # neighbouring rows
+        assert abs(frac - same) < 6 * (same * (1 - same) / cnt) ** 0.5, (frac, same)

@@ -73,6 +73,16 @@ def test_vq_one_million_latents_properties():
     z = torch.randn(1024, 8, 32, 32, generator=torch.Generator(device=DEV).manual_seed(5), device=DEV)
     z_q, _, (_, _, idx) = vq(z)
     assert idx.shape == (1 << 20,) and int(idx.min()) >= 0 and int(idx.max()) < 16384
+    # index for index against the reference algorithm (the [chunk, 16384] distance matrix + argmin, 16 chunks of 65 536
+    # latents) run on this GPU.  The library's fp32 GEMM sums in another order than the kernel, so a disagreement is
+    # legitimate only where the two best codes tie to within fp32 rounding of d -- verified in fp64, and counted.
+    _, ref = OV.quantize(z, cb.to(DEV), chunk=65536)
+    mism = (idx != ref).nonzero().flatten()
+    if mism.numel():
+        zn64 = torch.nn.functional.normalize(z.permute(0, 2, 3, 1).reshape(-1, 8)[mism].double(), dim=-1)
+        en64 = torch.nn.functional.normalize(cb.to(DEV).double(), dim=-1)
+        gap = ((zn64 * en64[idx[mism]]).sum(-1) - (zn64 * en64[ref[mism]]).sum(-1)).abs() * 2
+        assert mism.numel() <= 4 and float(gap.max()) < 2.5e-7, (mism.numel(), float(gap.max()), mism[:5].tolist())
     # idempotence: quantising the quantised latents returns the same codes
     _, _, (_, _, idx2) = vq(z_q)
     assert torch.equal(idx, idx2)
@@ -87,6 +97,36 @@ def test_vq_one_million_latents_properties():
     perm = torch.randperm(1024, generator=torch.Generator().manual_seed(1)).to(DEV)
     _, _, (_, _, idx_p) = vq(z[perm].contiguous())
     assert torch.equal(idx_p.view(1024, -1), idx.view(1024, -1)[perm])
+
+
+def test_vqmodel_encode_and_decode_code_vs_reference_fixture(golden):
+    """The tokenizer surface the samplers call (vq_model.py:41-55): VQ_models['VQ-16'] rebuilt from the seed, encode() ->
+    the index search kernel, decode_code() -> fused gather + post_quant_conv kernel -> decoder CNN (library convolutions,
+    fp32, TF32 off).  Tolerances: the fused front is 8-term fp32 dot products (1e-5 absolute); the CNN outputs are compared
+    with the reference's CPU fp32 run at 1e-3 of the output range (summation order of cuDNN vs MKL-DNN over ~30 layers)."""
+    from vlg.vq_model import VQ_models
+    f = golden("vqmodel.npz")
+    torch.manual_seed(0)
+    m = VQ_models["VQ-16"](codebook_size=16384, codebook_embed_dim=8).eval().to(DEV)
+    x = torch.from_numpy(f["x"]).to(DEV)
+    with torch.no_grad():
+        h = m.quant_conv(m.encoder(x))
+        quant, _, (_, _, idx) = m.encode(x)
+    assert float((h.cpu() - torch.from_numpy(f["h"])).abs().max()) < 1e-3 * float(np.abs(f["h"]).max())
+    _, ref_idx = OV.quantize(h.cpu(), m.quantize.embedding.weight.detach().cpu())
+    assert torch.equal(idx.cpu(), ref_idx)                             # bit-exact on the same encoder output
+    assert (idx.cpu().numpy() == f["idx"]).mean() >= 0.9               # the fixture's h differs in the last bits
+    assert quant.shape == (2, 8, 4, 4)
+    codes = torch.from_numpy(f["codes"]).to(DEV)
+    feat = m.quantize.decode_front(codes, (2, 8, 8, 8), m.post_quant_conv.weight, m.post_quant_conv.bias)
+    assert float((feat.cpu() - torch.from_numpy(f["feat"])).abs().max()) < 1e-5
+    with torch.no_grad():
+        img = m.decode_code(codes, (2, 8, 8, 8))
+        img2 = m.decode(m.quantize.get_codebook_entry(codes, (2, 8, 8, 8)))
+    rng = float(np.abs(f["img"]).max())
+    assert img.shape == (2, 3, 128, 128)
+    assert float((img.cpu() - torch.from_numpy(f["img"])).abs().max()) < 1e-3 * rng
+    assert float((img - img2).abs().max()) < 1e-4 * rng               # fused front == gather followed by the 1x1 conv
 
 
 # ------------------------------------------------------------------------------------------ RMSNorm
@@ -251,3 +291,74 @@ def test_in_kernel_philox_draws_follow_the_distribution():
     freq = torch.bincount(a.flatten().cpu(), minlength=V).double() / B
     chi2 = float((((freq - p.double()) ** 2) / p.double()).sum() * B)
     assert chi2 < 130, chi2                                           # 63 dof: P(chi2 > 130) ~ 1e-6
+
+
+# ---- the kernel branch the in-library decode loop runs (probs_out == NULL, noise == NULL, sample_logits == 1:
+#      4-wide Philox counters, log-domain race without the softmax denominator) -- sample.cu, `exact == false`
+def _chi2(tokens, p, n):
+    freq = torch.bincount(tokens.flatten().cpu(), minlength=p.numel()).double()
+    keep = p > 0
+    assert int(freq[~keep].sum()) == 0, "a filtered-out token was drawn"
+    e = p[keep].double() * n
+    return float((((freq[keep] - e) ** 2) / e).sum()), int(keep.sum()) - 1
+
+
+def test_loop_branch_draws_follow_the_distribution():
+    V, B = 64, 4096
+    p = torch.softmax(torch.randn(V, generator=torch.Generator().manual_seed(0)) * 1.5, dim=0)
+    logits = torch.log(p).repeat(B, 1).to(DEV).contiguous()
+    a, pa = G._run_sampler(logits, B, B, 1.0, 0, 1.0, 0, 1.0, True, seed=11, want_probs=False)
+    b, _ = G._run_sampler(logits, B, B, 1.0, 0, 1.0, 0, 1.0, True, seed=11, want_probs=False)
+    c, _ = G._run_sampler(logits, B, B, 1.0, 0, 1.0, 0, 1.0, True, seed=12, want_probs=False)
+    d, _ = G._run_sampler(logits, B, B, 1.0, 0, 1.0, 0, 1.0, True, seed=11, want_probs=False, offset=1)
+    assert pa is None
+    assert torch.equal(a, b) and not torch.equal(a, c) and not torch.equal(a, d)
+    chi2, dof = _chi2(a, p, B)
+    assert chi2 < 130, (chi2, dof)                                    # 63 dof: P(chi2 > 130) ~ 1e-6
+    # rows (CTAs) and steps (offsets) are independent streams: the same token in two of them happens with prob sum(p^2)
+    same = float(p.pow(2).sum())
+    for x, y in ((a, d), (a[:-1], a[1:])):
+        frac = float((x == y).float().mean())
+        assert abs(frac - same) < 6 * (same * (1 - same) / B) ** 0.5, (frac, same)
+
+
+def test_loop_branch_full_size_topk_cfg():
+    """cfg-2 sampler shape: V = 16384, CFG 4.0 over 2B rows, top-k 2000: the loop branch draws from the filtered softmax
+    and never picks a removed token.  Chi-square over probability-rank bins ([0], [1], [2,4), [4,8) ... [1024, 2000)) pooled
+    over the 64 rows x 128 steps, so that every cell expects hundreds of draws."""
+    g = torch.Generator().manual_seed(5)
+    B, V, reps = 64, 16384, 128
+    logits = (torch.randn(2 * B, 1, V, generator=g) * 0.5).bfloat16().float()
+    _, ref_p = O.sample(O.cfg_mix(logits, 4.0).clone(), temperature=1.0, top_k=2000, top_p=1.0, sample_logits=False)
+    dl = logits[:, 0].contiguous().to(DEV)
+    draws = torch.stack([G._run_sampler(dl, 2 * B, B, 4.0, 1, 1.0, 2000, 1.0, True, seed=3, want_probs=False, offset=s)[0]
+                         .flatten().cpu() for s in range(reps)], dim=1)          # [B, reps]
+    assert bool((ref_p.gather(1, draws) > 0).all()), "a token outside the top-k set was drawn"
+    order = ref_p.argsort(dim=1, descending=True, stable=True)
+    rank = torch.empty_like(order)
+    rank.scatter_(1, order, torch.arange(V).expand(B, V))
+    edges = [0, 1, 2, 4, 8, 16, 32, 64, 128, 256, 512, 1024, V]
+    psort = ref_p.gather(1, order).double()
+    drank = rank.gather(1, draws)
+    chi2 = 0.0
+    for lo, hi in zip(edges[:-1], edges[1:]):
+        e = float(psort[:, lo:hi].sum()) * reps
+        c = float(((drank >= lo) & (drank < hi)).sum())
+        assert e > 50, (lo, hi, e)
+        chi2 += (c - e) ** 2 / e
+    assert chi2 < 45, chi2                                             # 11 dof: P(chi2 > 45) ~ 5e-6
+
+
+def test_loop_branch_equals_api_branch_for_the_same_seed_and_step():
+    """Same Philox counters in both branches: argmax(p / E) (IEEE divisions, API) and argmax((x - max) - log E)
+    (decode loop, __logf) pick the same token except on near-ties of the two largest scores."""
+    g = torch.Generator().manual_seed(9)
+    B, V = 64, 16384
+    dl = (torch.randn(2 * B, V, generator=g) * 2).bfloat16().float().to(DEV)
+    agree = n = 0
+    for step in range(24):
+        a, _ = G._run_sampler(dl, 2 * B, B, 4.0, 1, 1.0, 2000, 1.0, True, seed=77, want_probs=True, offset=step)
+        b, _ = G._run_sampler(dl, 2 * B, B, 4.0, 1, 1.0, 2000, 1.0, True, seed=77, want_probs=False, offset=step)
+        agree += int((a == b).sum())
+        n += B
+    assert agree >= n - 3, (agree, n)      # __logf is good to ~1e-6 relative: a flip needs a ~1e-6 near-tie of the top 2

@@ -79,3 +79,44 @@ def test_bench_reference_arm_prints_one_contract_line():
     assert d["impl"] == "reference" and d["unit"] == "tokens/s" and d["higher_is_better"] is True and d["value"] > 0
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["e2e"]["h2d_bytes_per_step"] == 0
     assert d["config"]["workload"].startswith("cfg-2") and d["metric"].startswith("generated visual tokens/sec")
+
+
+def test_sample_script_import_lines_resolve_to_the_drop_ins():
+    """The import lines of the reference's samplers that belong to the path (autoregressive/sample/sample_t2i.py:24-27,
+    serve/sample_c2i.py:6; `language.t5` on :25 is the reference's own T5 wrapper and stays the reference's)."""
+    from tokenizer.tokenizer_image.vq_model import VQ_models
+    from autoregressive.models.gpt import GPT_models
+    from autoregressive.models.generate import generate
+    import vlg.vq_model, vlg.gpt, vlg.generate
+    assert VQ_models is vlg.vq_model.VQ_models and set(VQ_models) == {"VQ-16", "VQ-8"}
+    assert GPT_models is vlg.gpt.GPT_models and generate is vlg.generate.generate
+    vq = VQ_models["VQ-8"](codebook_size=64, codebook_embed_dim=8)          # ctor kwargs of sample_t2i.py:41-43
+    assert {"quantize.embedding.weight", "quantize.codebook_used", "quant_conv.weight", "post_quant_conv.bias",
+            "encoder.conv_in.weight", "decoder.conv_out.bias", "decoder.conv_blocks.0.attn.2.proj_out.weight",
+            "decoder.conv_blocks.1.upsample.conv.weight", "encoder.conv_blocks.0.downsample.conv.bias",
+            "encoder.mid.1.q.weight", "decoder.conv_blocks.3.res.0.nin_shortcut.weight"} <= set(vq.state_dict())
+    assert vq.quantize.codebook_used.shape == (65536,)
+    for name in ("encode", "decode", "decode_code", "forward"):
+        assert callable(getattr(vq, name))
+
+
+def test_vqmodel_same_seed_same_weights_and_cnn_parity(golden):
+    """VQ_models['VQ-16'] consumes torch's RNG like the reference's constructor (same keys, same weights per seed), and
+    its encoder / decoder CNNs (library convolutions) reproduce the reference module's outputs on CPU fp32."""
+    f = golden("vqmodel.npz")
+    from vlg.vq_model import VQ_models
+    torch.manual_seed(0)
+    m = VQ_models["VQ-16"](codebook_size=16384, codebook_embed_dim=8).eval()
+    sd = m.state_dict()
+    assert {"sum." + k for k in sd} == {k for k in f.files if k.startswith("sum.")}
+    for k, v in sd.items():
+        s = f["sum." + k]
+        assert abs(float(v.double().sum()) - s[0]) < 1e-6 and abs(float(v.double().abs().sum()) - s[1]) < 1e-6, k
+    with torch.no_grad():
+        h = m.quant_conv(m.encoder(torch.from_numpy(f["x"])))
+        img = m.decoder(torch.from_numpy(f["feat"]))
+    assert np.abs(h.numpy() - f["h"]).max() < 1e-4 * max(1.0, np.abs(f["h"]).max())
+    assert np.abs(img.numpy() - f["img"]).max() < 1e-4 * max(1.0, np.abs(f["img"]).max())
+    if not torch.cuda.is_available():
+        with pytest.raises(_lib.VlgError):
+            m.decode_code(torch.from_numpy(f["codes"]), (2, 8, 8, 8))

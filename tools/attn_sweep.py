@@ -1,5 +1,5 @@
 """Microbenchmark: attention kernel time vs cache position (fixed overhead and marginal bandwidth).
-   python tools/attn_sweep.py [impl]   (impl 2 = TMA kernel, 1 = generic)"""
+   python tools/attn_sweep.py [impl] [regions]   (impl 2 = TMA kernel, 1 = generic)"""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "video-llamagen_b200")]
@@ -10,7 +10,7 @@ impl = int(sys.argv[1]) if len(sys.argv) > 1 else 2
 rows, H, D, S_max = 128, 16, 64, 584
 dev = "cuda"
 g = torch.Generator(device=dev).manual_seed(0)
-regions = 6
+regions = int(sys.argv[2]) if len(sys.argv) > 2 else 6     # 1 = the same K/V region every launch (L2-hot when it fits)
 q = torch.randn(rows, H, D, device=dev, generator=g).bfloat16()
 ks = [torch.randn(rows, H, S_max, D, device=dev, generator=g).bfloat16() for _ in range(regions)]
 vs = [torch.randn(rows, H, S_max, D, device=dev, generator=g).bfloat16() for _ in range(regions)]

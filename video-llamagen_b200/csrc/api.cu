@@ -16,11 +16,12 @@ using namespace vlg;
 
 namespace {
 
-struct StepState {      // device-resident loop state (ints)
+struct StepState {      // device-resident loop state
   int step;             // index of the token being produced (column of seq)
   int pos;              // cache slot / RoPE row of the current input
   unsigned done_ctr;    // sampler CTA completion counter
   int pad;
+  unsigned long long seed;   // Philox seed of the current generate(): read by the sampler, so the captured graph does not bake it in
 };
 
 size_t esz(int dtype) { return dtype == VLG_BF16 ? 2 : 4; }
@@ -89,13 +90,17 @@ struct vlg_ctx {
   // graph capture is illegal on the legacy default stream (torch's default): such callers are forked onto this one
   cudaStream_t own_stream = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  // grid-barrier timeout flag of the layer-tail kernel: one word of mapped pinned host memory the device writes and the
+  // host reads without synchronising (ctx_check)
+  unsigned* err_host = nullptr;
+  unsigned* err_dev = nullptr;
   // cached decode-step graph
   cudaGraphExec_t graph = nullptr;
   cudaGraphExec_t graph_v = nullptr;   // t2v decode step (vlg_generate_t2v)
   struct KeyV { int rows, B, N, cfg_interval, has_mask; float cfg_scale; void* out; } key_v{};
   uint64_t step_kernels_v = 0;
   uint64_t step_kernels = 0;   // kernels per replayed decode step
-  struct Key { int rows, B, N, top_k, sample_logits, cfg_interval, has_mask; float cfg_scale, temperature, top_p; uint64_t seed; } key{};
+  struct Key { int rows, B, N, top_k, sample_logits, cfg_interval, has_mask; float cfg_scale, temperature, top_p; } key{};
 
   template <typename T> T* at(size_t off) const { return reinterpret_cast<T*>(ws + off); }
   void* kc(int layer) const { return ws + L.k_cache + (size_t)layer * max_rows * g.n_head * S_max * D * esz(g.dtype); }
@@ -105,10 +110,23 @@ struct vlg_ctx {
 
 namespace {
 
-__global__ void set_state_kernel(StepState* s, int step, int pos) {
+// A layer-tail launch of this context gave up in a grid barrier (its CTAs were not all resident: something else was
+// occupying SMs).  Results since then are garbage; report it once and re-arm the counters.
+int ctx_check(vlg_ctx* c) {
+  if (c->err_host == nullptr || *reinterpret_cast<volatile unsigned*>(c->err_host) == 0) return VLG_OK;
+  cudaDeviceSynchronize();
+  *c->err_host = 0;
+  cudaMemset(c->ws + c->L.lt_bar, 0, 2 * sizeof(unsigned));
+  set_error("a layer-tail launch timed out in its grid barrier: its %d CTAs were not co-resident (another context, stream or "
+            "process was occupying SMs of this GPU); outputs since the previous successful call are invalid", num_sms());
+  return VLG_ERR_STATE;
+}
+
+__global__ void set_state_kernel(StepState* s, int step, int pos, unsigned long long seed) {
   s->step = step;
   s->pos = pos;
   s->done_ctr = 0;
+  s->seed = seed;
 }
 
 // rows [0,B) <- cond[b], rows [B,2B) <- uncond (broadcast): generate.py:137-139
@@ -193,9 +211,18 @@ int run_trunk(vlg_ctx* c, const int* pos_ptr, int pos_imm, int max_pos, bool fus
     t.part = c->at<float>(c->L.lt_part);
     t.part_bytes = layer_tail_scratch_bytes(c->max_rows, d, hid);
     t.bar = c->at<unsigned>(c->L.lt_bar);
+    t.err = c->err_dev;
     int rc;
+    // what the launch in front of layer l's attention asks L2 to fetch meanwhile: that attention's K/V prefix
+    auto prefetch_kv = [&](LtLaunch& m, int l) {
+      if (c->skip_attention) return;
+      m.pf_k = c->kc(l); m.pf_v = c->vc(l);
+      m.pf_n_rh = R * g.n_head; m.pf_stride_bytes = (long long)c->S_max * c->D * 2;
+      m.pf_pos_ptr = pos_ptr; m.pf_pos_imm = pos_imm;
+    };
     LtLaunch f = t;
     f.norm2_w = c->layers[0].attention_norm; f.wqkv = c->layers[0].wqkv; f.rope = rope_params(0);
+    prefetch_kv(f, 0);
     if ((rc = launch_layer_tail(f, st))) return rc;
     for (int l = 0; l < g.n_layer; ++l) {
       const vlg_layer_weights& lw = c->layers[l];
@@ -214,8 +241,12 @@ int run_trunk(vlg_ctx* c, const int* pos_ptr, int pos_imm, int max_pos, bool fus
       m.wo = lw.wo; m.w13 = lw.w13; m.w2 = lw.w2; m.norm1_w = lw.ffn_norm;
       if (l + 1 < g.n_layer) {
         m.norm2_w = c->layers[l + 1].attention_norm; m.wqkv = c->layers[l + 1].wqkv; m.rope = rope_params(l + 1);
+        prefetch_kv(m, l + 1);
       } else {
         m.norm2_w = c->w.norm;
+        if (fuse_final && c->w.output && g.vocab_size > 0 && !c->skip_attention) {   // the head GEMM follows: its weights
+          m.pf_flat = c->w.output; m.pf_flat_bytes = (size_t)g.vocab_size * d * 2;
+        }
       }
       if ((rc = launch_layer_tail(m, st))) return rc;
     }
@@ -337,7 +368,8 @@ SampleArgs loop_sample_args(vlg_ctx* c, const vlg_generate_params& p) {
   a.p.top_k = p.top_k;
   a.p.top_p = p.top_p;
   a.p.sample_logits = p.sample_logits;
-  a.p.seed = p.seed;
+  a.p.seed = 0;                                   // the loop reads the seed from the device state (graph reuse across seeds)
+  a.seed_ptr = &c->state()->seed;
   a.p.offset = 0;
   a.seq_out = c->at<int32_t>(c->L.seq);
   a.seq_stride = p.max_new_tokens;
@@ -406,6 +438,9 @@ extern "C" int vlg_ctx_create(const vlg_geometry* g, const vlg_weights* w, int m
   VLG_CUDA(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
   VLG_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
   VLG_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+  VLG_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&c->err_host), sizeof(unsigned), cudaHostAllocMapped));
+  *c->err_host = 0;
+  VLG_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&c->err_dev), c->err_host, 0));
   // the reference allocates zeroed caches (gpt.py:174-175); do it once so no stale NaN bit patterns exist
   VLG_CUDA(cudaMemset(c->ws + L.k_cache, 0, L.h - L.k_cache));
   VLG_CUDA(cudaMemset(c->state(), 0, sizeof(StepState)));
@@ -422,19 +457,21 @@ extern "C" void vlg_ctx_destroy(vlg_ctx* c) {
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
   if (c->ev_fork) cudaEventDestroy(c->ev_fork);
   if (c->ev_join) cudaEventDestroy(c->ev_join);
+  if (c->err_host) cudaFreeHost(c->err_host);
   delete c;
 }
 
 extern "C" int vlg_begin(vlg_ctx* c, int rows, const uint8_t* prefix_mask_dev, void* stream) {
   VLG_REQUIRE(c, "vlg_begin: null ctx");
   VLG_REQUIRE(rows > 0 && rows <= c->max_rows, "vlg_begin: rows %d outside (0, %d]", rows, c->max_rows);
+  if (int rc = ctx_check(c)) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   c->rows = rows;
   c->has_mask = prefix_mask_dev != nullptr;
   if (prefix_mask_dev)
     VLG_CUDA(cudaMemcpyAsync(c->at<uint8_t>(c->L.mask), prefix_mask_dev, (size_t)rows * c->g.cls_token_num,
                              cudaMemcpyDeviceToDevice, st));
-  set_state_kernel<<<1, 1, 0, st>>>(c->state(), 0, 0);
+  set_state_kernel<<<1, 1, 0, st>>>(c->state(), 0, 0, 0ull);
   VLG_LAUNCH_CHECK();
   return VLG_OK;
 }
@@ -447,7 +484,8 @@ extern "C" int vlg_forward_pos(vlg_ctx* c, const int64_t* tokens_dev, const int6
   VLG_REQUIRE(pos >= 0 && pos < c->S_max && pos < c->w.rope_rows, "vlg_forward_pos: pos %d out of range", pos);
   cudaStream_t st = (cudaStream_t)stream;
   const vlg_geometry& g = c->g;
-  int rc = VLG_OK;
+  int rc = ctx_check(c);
+  if (rc) return rc;
   if (tokens_dev) {
     VLG_REQUIRE(c->w.tok_embeddings, "vlg_forward_pos: no tok_embeddings");
     rc = launch_gather(g.dtype, c->w.tok_embeddings, c->at<void>(c->L.h), c->rows, g.dim, tokens_dev, nullptr, 0,
@@ -509,6 +547,7 @@ static int generate_on(vlg_ctx* c, const vlg_generate_params* pp, const void* co
 extern "C" int vlg_generate(vlg_ctx* c, const vlg_generate_params* pp, const void* cond_dev, const void* uncond_dev,
                             const uint8_t* emb_masks_dev, int32_t* tokens_dev, void* stream) {
   VLG_REQUIRE(c && pp && cond_dev && tokens_dev, "vlg_generate: null pointer");
+  if (int rc0 = ctx_check(c)) return rc0;
   cudaStream_t user = (cudaStream_t)stream;
   const bool legacy = user == nullptr || user == cudaStreamLegacy || user == cudaStreamPerThread;
   if (!legacy) return generate_on(c, pp, cond_dev, uncond_dev, emb_masks_dev, tokens_dev, user);
@@ -540,7 +579,7 @@ static int generate_on(vlg_ctx* c, const vlg_generate_params* pp, const void* co
     build_mask_rows_kernel<<<(rows * T + 255) / 256, 256, 0, st>>>(emb_masks_dev, c->at<uint8_t>(c->L.mask), p.B, T, rows);
     VLG_LAUNCH_CHECK();
   }
-  set_state_kernel<<<1, 1, 0, st>>>(c->state(), 0, T - 1);
+  set_state_kernel<<<1, 1, 0, st>>>(c->state(), 0, T - 1, (unsigned long long)p.seed);
   VLG_LAUNCH_CHECK();
 
   // ---- prefill (generate.py:77-86): every conditioning position through the trunk, sample from the last
@@ -581,7 +620,7 @@ static int generate_on(vlg_ctx* c, const vlg_generate_params* pp, const void* co
 
   // ---- decode loop (generate.py:105-124) as a replayed CUDA graph
   if (N > 1) {
-    vlg_ctx::Key k{rows, p.B, N, p.top_k, p.sample_logits, p.cfg_interval, c->has_mask ? 1 : 0, p.cfg_scale, p.temperature, p.top_p, p.seed};
+    vlg_ctx::Key k{rows, p.B, N, p.top_k, p.sample_logits, p.cfg_interval, c->has_mask ? 1 : 0, p.cfg_scale, p.temperature, p.top_p};
     if (!c->graph || memcmp(&k, &c->key, sizeof(k)) != 0) {
       if (c->graph) { cudaGraphExecDestroy(c->graph); c->graph = nullptr; }
       cudaGraph_t graph = nullptr;
@@ -671,7 +710,7 @@ int generate_t2v_on(vlg_ctx* c, const vlg_generate_params* pp, const void* cond_
     build_mask_rows_kernel<<<(rows * T + 255) / 256, 256, 0, st>>>(emb_masks_dev, c->at<uint8_t>(c->L.mask), p.B, T, rows);
     VLG_LAUNCH_CHECK();
   }
-  set_state_kernel<<<1, 1, 0, st>>>(c->state(), 0, T - 1);
+  set_state_kernel<<<1, 1, 0, st>>>(c->state(), 0, T - 1, 0ull);
   VLG_LAUNCH_CHECK();
   VLG_CUDA(cudaMemsetAsync(c->at<void>(c->L.lat_in), 0, (size_t)rows * ld_in * esz(g.dtype), st));   // the padding columns stay zero
 
@@ -734,6 +773,7 @@ extern "C" int vlg_generate_t2v(vlg_ctx* c, const vlg_generate_params* pp, const
                                 const uint8_t* emb_masks_dev, void* latents_dev, void* stream) {
   VLG_REQUIRE(c && pp && cond_dev && latents_dev, "vlg_generate_t2v: null pointer");
   VLG_REQUIRE(c->g.model_type == VLG_T2V, "vlg_generate_t2v: model type %d is not t2v", c->g.model_type);
+  if (int rc0 = ctx_check(c)) return rc0;
   cudaStream_t user = (cudaStream_t)stream;
   const bool legacy = user == nullptr || user == cudaStreamLegacy || user == cudaStreamPerThread;
   if (!legacy) return generate_t2v_on(c, pp, cond_dev, uncond_dev, emb_masks_dev, latents_dev, user);
@@ -759,7 +799,13 @@ extern "C" int vlg_generate_c2i_host(vlg_ctx* c, const vlg_generate_params* p, c
   if (rc) return rc;
   VLG_CUDA(cudaMemcpyAsync(tokens_host, seq, (size_t)p->B * p->max_new_tokens * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
   VLG_CUDA(cudaStreamSynchronize(st));
-  return VLG_OK;
+  return ctx_check(c);
+}
+
+extern "C" int vlg_ctx_check(vlg_ctx* c, void* stream) {
+  VLG_REQUIRE(c, "vlg_ctx_check: null ctx");
+  VLG_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  return ctx_check(c);
 }
 
 extern "C" int vlg_attn_decode(const void* q_dev, const void* k_cache_dev, const void* v_cache_dev, void* out_dev,

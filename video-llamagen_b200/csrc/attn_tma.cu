@@ -388,16 +388,19 @@ int launch_attn_tma(int dtype, const AttnArgs& a, cudaStream_t st) {
     VLG_REQUIRE(a.scratch && a.scratch_bytes >= (size_t)n_rh * n_splits * 66 * sizeof(float),
                 "attn(tma): scratch too small for %d splits", n_splits);
   const int smem = (int)sizeof(AttnTmaSmem) + 1024;
-  static bool attr_set = false;
-  if (!attr_set) {
-    VLG_CUDA(cudaFuncSetAttribute(attn_decode_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_set = true;
-  }
+  static PerDeviceOnce attr_once;
+  VLG_CUDA(attr_once([&] { return cudaFuncSetAttribute(attn_decode_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); }));
   const int n_items = n_rh * n_splits;
   const int grid = n_items < sms ? n_items : sms;
+  // Early streaming (before griddepcontrol.wait) reads the position word and cache rows that earlier decode steps wrote.
+  // Only a captured graph orders those writes before this launch for certain (consecutive graph launches serialise);
+  // on a plain stream the programmatic-launch chain lets this kernel's prologue run while a kernel two places back is
+  // still executing, so the shortcut is off there.
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  const bool early = a.early_prefetch && cudaStreamIsCapturing(st, &cap) == cudaSuccess && cap == cudaStreamCaptureStatusActive;
   VLG_CUDA(launch_kernel(attn_decode_tma_kernel, dim3(grid), dim3(kAttnTmaThreads), (size_t)smem, st, tmK, tmV,
                          (const __nv_bfloat16*)a.q, (__nv_bfloat16*)a.out, a.scratch, n_rh, a.H, a.S_max, a.pos_ptr,
-                         a.pos_imm, a.prefix_mask, a.T_prefix, n_splits, a.early_prefetch ? 1 : 0));
+                         a.pos_imm, a.prefix_mask, a.T_prefix, n_splits, early ? 1 : 0));
   VLG_LAUNCH_CHECK();
   if (n_splits > 1) {
     VLG_CUDA(launch_kernel(attn_tma_combine_kernel, dim3(n_rh), dim3(64), 0, st, (const float*)a.scratch,

@@ -233,6 +233,19 @@ struct alignas(64) TensorMap { uint8_t bytes[128]; };
 int make_tmap_bf16_2d(TensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t row_stride_bytes,
                       uint32_t box_rows, uint32_t box_cols, bool swizzle128);
 
-int num_sms();
+int num_sms();                       // SM count of the current device
+constexpr int kMaxDevices = 64;
+int current_device();                // cudaGetDevice clamped to [0, kMaxDevices)
+// cudaFuncSetAttribute is per device: run `set` once for every (call site, device)
+struct PerDeviceOnce {
+  bool done[kMaxDevices] = {};
+  template <typename F> cudaError_t operator()(F&& set) {
+    const int d = current_device();
+    if (done[d]) return cudaSuccess;
+    cudaError_t e = set();
+    if (e == cudaSuccess) done[d] = true;
+    return e;
+  }
+};
 
 }  // namespace vlg

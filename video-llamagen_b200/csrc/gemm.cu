@@ -235,11 +235,8 @@ static int launch_tc(const void* x, const void* w, int rows, int N, int K, const
   rc = make_tmap_bf16_2d(&tmB, w, (uint64_t)N, (uint64_t)K, (uint64_t)K * 2, BN, kBK, true);
   if (rc) return rc;
   auto kern = gemm_bf16_tc_kernel<BM, BN, EPI>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    VLG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    attr_set = true;
-  }
+  static PerDeviceOnce attr_once;
+  VLG_CUDA(attr_once([&] { return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes); }));
   dim3 grid(N / BN, (rows + BM - 1) / BM);
   static const int dbg = [] { const char* e = getenv("VLG_GEMM_DEBUG"); return e ? atoi(e) : 0; }();
   VLG_CUDA(launch_kernel(kern, grid, dim3(kGemmThreads), Cfg::kSmemBytes, st, tmA, tmB, rows, K, P, dbg));

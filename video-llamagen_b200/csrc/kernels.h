@@ -58,6 +58,15 @@ struct LtLaunch {
   float* part;          // split-K scratch, layer_tail_scratch_bytes()
   size_t part_bytes;
   unsigned* bar;        // 2 counters, zero
+  unsigned* err = nullptr;   // device-visible pointer to a mapped host word: grid-barrier timeout flag (may be null)
+  // optional L2 prefetch for the kernel that follows (layer_tail.cu, lt_pf_slice): next layer's K/V prefix rows [0, pos)
+  const void *pf_k = nullptr, *pf_v = nullptr;
+  int pf_n_rh = 0;
+  long long pf_stride_bytes = 0;
+  const int* pf_pos_ptr = nullptr;
+  int pf_pos_imm = 0;
+  const void* pf_flat = nullptr;   // and / or one flat region (head weights)
+  size_t pf_flat_bytes = 0;
 };
 bool layer_tail_supported(int rows, int dim, int hidden);
 size_t layer_tail_scratch_bytes(int max_rows, int dim, int hidden);
@@ -79,6 +88,7 @@ struct SampleArgs {
   int* pos_ptr;         // device cache position: incremented together with the step
   int cfg_interval;     // -1: always guided
   unsigned* done_ctr;   // block-completion counter for the increment
+  const unsigned long long* seed_ptr;   // device-resident Philox seed (overrides p.seed when non-null)
 };
 int launch_sample(const SampleArgs& a, cudaStream_t st);
 

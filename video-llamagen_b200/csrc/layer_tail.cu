@@ -71,7 +71,20 @@ struct LtParams {
   EpiParams ffn;             // SwiGLU destination (out, ld_out)
   EpiParams rope;            // RoPE + cache append parameters
   unsigned* bar;             // [0] grid-barrier arrivals, [1] exit arrivals; both zero between launches
+  volatile unsigned* err;    // mapped host word: set when a grid barrier gave up waiting (see lt_grid_barrier)
   int dbg;
+  int fast_silu;             // SwiGLU epilogue: ex2.approx / rcp.approx instead of expf + IEEE division (A/B: VLG_LT_FASTSILU)
+  // L2 prefetch of what the NEXT kernel streams from HBM (see lt_pf_slice): the K/V prefix of the next layer's attention,
+  // and/or one flat region (the head GEMM's weights after the last layer)
+  const uint8_t* pf_k;       // next layer's K cache [n_rh][S_max][128 B]
+  const uint8_t* pf_v;
+  int pf_n_rh;               // rows * heads
+  long long pf_stride;       // bytes between (row, head) spans = S_max * 128
+  const int* pf_pos_ptr;     // device cache position (rows [0, pos) of every span are complete), or null -> pf_pos_imm
+  int pf_pos_imm;
+  long long pf_budget;       // bytes of K + V to request per launch (0 = off)
+  const uint8_t* pf_flat;    // flat region, pf_flat_bytes long
+  long long pf_flat_bytes;
 };
 
 // phase timestamps (globaltimer ns) of every CTA of the last full (front + qkv) launch, VLG_LT_DEBUG=1: instrumentation
@@ -123,19 +136,35 @@ __device__ __forceinline__ uint4 ldg128_cg(const void* p) {
 }
 
 // All CTAs of the grid are co-resident (grid <= SM count, one CTA per SM): arrive with a release add, poll with acquire.
-__device__ __forceinline__ void lt_grid_barrier(unsigned* ctr, unsigned& target) {
+// Co-residency holds whenever this context has the GPU's SMs to itself; if some other resident work keeps CTAs of this grid
+// from being scheduled, the wait is bounded (2 s of globaltimer) and ends in an error word in mapped host memory that the
+// host turns into VLG_ERR_STATE on its next call -- never in a trap that would poison the CUDA context.  Once the word is
+// set every later barrier of every CTA falls through at once, so a contended launch drains in seconds, not minutes.
+__device__ __forceinline__ void lt_grid_barrier(unsigned* ctr, unsigned& target, volatile unsigned* err) {
   target += gridDim.x;
   tc_fence_before();
   __syncthreads();
   if (threadIdx.x == 0) {
     // release: cumulative over the CTA's stores ordered before it by the bar.sync above (tools/micro/bar_bench.cu: the
-    // extra fences of the cooperative-groups recipe cost 0.25 us per barrier and add nothing to this pattern)
+    // extra fences of the cooperative-groups recipe cost 0.25 us per barrier and add nothing to this pattern;
+    // tools/micro/bar_bench2.cu: moving the pollers off the counter's line onto flag lines is slower, 1.8-2.0 vs 1.25 us)
     asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
     unsigned seen, spins = 0;
-    do {
+    unsigned long long t0 = 0;
+    for (;;) {
       asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(ctr) : "memory");
-      if (++spins > (1u << 25)) { printf("vlg: layer-tail grid barrier timeout (block %d, %u < %u)\n", blockIdx.x, seen, target); __trap(); }
-    } while (seen < target);
+      if (seen >= target) break;
+      if ((++spins & 1023u) == 0) {
+        unsigned long long now;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        if (t0 == 0) t0 = now;
+        if (err != nullptr && *err != 0) break;                       // somebody already gave up
+        if (now - t0 > 2000000000ull) {
+          if (err != nullptr) { *err = 1u; __threadfence_system(); }
+          break;
+        }
+      }
+    }
   }
   __syncthreads();
   tc_fence_after();
@@ -147,6 +176,56 @@ template <int ST> struct LtSmem {
   uint32_t tmem_slot;
   float red[kLtThreads / 32];
 };
+
+// ---------------------------------------------------------------------------------------------------- L2 prefetch
+// This kernel is latency-bound (grid barriers, dependent phases) and keeps HBM busy for ~4 of its ~25 us, while the attention
+// kernel that follows is HBM-bound.  So the last warp of every CTA spends the idle HBM time pulling the leading part of the
+// next layer's K/V prefix into L2 (cp.async.bulk.prefetch.L2: fire-and-forget, no shared memory, no completion to wait
+// for): the attention kernel then finds a mix of L2 hits and HBM misses in its TMA ring and streams at the sum of both
+// rates.  Rows [0, pos) of the next layer's cache were written in earlier decode steps, so nothing here is ordered against
+// this launch's own writes (row `pos` is written by the wqkv epilogue below and is not requested).  One slice per phase
+// paces the requests over the whole launch so that they do not queue in front of this kernel's own operand loads.
+__device__ __forceinline__ void bulk_prefetch_l2(const void* p, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void lt_pf_slice(const LtParams& P, int slice, int n_slices) {
+  if (threadIdx.x < kLtThreads - 32) return;            // the last warp: it owns no GEMM role
+  const int lane = threadIdx.x & 31;
+  constexpr long long kSub = 2048;
+  if (P.pf_budget > 0 && P.pf_k != nullptr) {
+    const int pos = P.pf_pos_ptr ? *P.pf_pos_ptr : P.pf_pos_imm;
+    const long long span = (long long)pos * 128;
+    const long long n_span = 2LL * P.pf_n_rh;
+    if (span > 0 && n_span > 0) {
+      long long per_span = n_span * span <= P.pf_budget ? span : ((P.pf_budget / n_span) & ~127LL);
+      const long long piece = ((per_span + n_slices - 1) / n_slices + 127) & ~127LL;
+      const long long off = (long long)slice * piece;
+      if (off < per_span) {
+        const long long len = per_span - off < piece ? per_span - off : piece;
+        const long long n_sub = (len + kSub - 1) / kSub;
+        const long long items = n_span * n_sub;
+        for (long long w = (long long)blockIdx.x * 32 + lane; w < items; w += 32LL * gridDim.x) {
+          const long long s = w / n_sub, c = w - s * n_sub;
+          const uint8_t* base = (s < P.pf_n_rh ? P.pf_k + s * P.pf_stride : P.pf_v + (s - P.pf_n_rh) * P.pf_stride) + off + c * kSub;
+          const long long b = len - c * kSub < kSub ? len - c * kSub : kSub;
+          bulk_prefetch_l2(base, (uint32_t)b);
+        }
+      }
+    }
+  }
+  if (P.pf_flat != nullptr && P.pf_flat_bytes > 0) {
+    const long long piece = ((P.pf_flat_bytes + n_slices - 1) / n_slices + kSub - 1) / kSub * kSub;
+    const long long off = (long long)slice * piece;
+    if (off < P.pf_flat_bytes) {
+      const long long len = P.pf_flat_bytes - off < piece ? P.pf_flat_bytes - off : piece;
+      const long long items = (len + kSub - 1) / kSub;
+      for (long long w = (long long)blockIdx.x * 32 + lane; w < items; w += 32LL * gridDim.x) {
+        const long long b = len - w * kSub < kSub ? len - w * kSub : kSub;
+        bulk_prefetch_l2(P.pf_flat + off + w * kSub, (uint32_t)(b & ~15LL));
+      }
+    }
+  }
+}
 
 // ---------------------------------------------------------------------------------------------------- GEMM phase
 // g: k-blocks this CTA has pushed through the ring so far (producer and MMA issuer walk the same sequence);
@@ -242,7 +321,9 @@ __device__ __forceinline__ void lt_gemm_phase(const LtGemm& G, const TensorMap* 
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
               const float a = rnd<__nv_bfloat16>(v[2 * i]), b = rnd<__nv_bfloat16>(v[2 * i + 1]);
-              o[i] = __fmul_rn(rnd<__nv_bfloat16>(silu_f(a)), b);
+              // fast form: 2-3 ulp of fp32 before the bf16 rounding of silu (2^-9 relative), instead of ~40 instructions
+              const float sl = P.fast_silu ? __fdividef(a, 1.0f + __expf(-a)) : silu_f(a);
+              o[i] = __fmul_rn(rnd<__nv_bfloat16>(sl), b);
             }
             stg256_bf16x16(static_cast<__nv_bfloat16*>(E.out) + (size_t)r * E.ld_out + ((u.n0 + c) >> 1), o);
           }
@@ -394,31 +475,40 @@ layer_tail_kernel(const __grid_constant__ TensorMap tmAttn, const __grid_constan
   pdl_wait();
   LT_TS(1);
 
+  const int pf_slices = (P.has_front ? 5 : 1) + (P.has_qkv ? 1 : 0);
+  int pf_i = 0;
   if (P.has_front) {
+    lt_pf_slice(P, pf_i++, pf_slices);
     lt_gemm_phase<-1, ST, SB>(P.g_wo, &tmAttn, &tmWo, &P.g_w13, &tmW13, P, P.ffn, ring, sm, tmem_acc, g, acc_uses, 16);
     LT_TS(2);
-    lt_grid_barrier(P.bar, bar_target);
+    lt_grid_barrier(P.bar, bar_target, P.err);
     LT_TS(3);
+    lt_pf_slice(P, pf_i++, pf_slices);
     lt_norm_phase(&P.g_wo, P.norm1_w, P, sm);
     LT_TS(4);
-    lt_grid_barrier(P.bar, bar_target);
+    lt_grid_barrier(P.bar, bar_target, P.err);
     LT_TS(5);
+    lt_pf_slice(P, pf_i++, pf_slices);
     lt_gemm_phase<EPI_SWIGLU, ST, SB>(P.g_w13, &tmXn, &tmW13, &P.g_w2, &tmW2, P, P.ffn, ring, sm, tmem_acc, g, acc_uses, 18);
     LT_TS(6);
-    lt_grid_barrier(P.bar, bar_target);
+    lt_grid_barrier(P.bar, bar_target, P.err);
     LT_TS(7);
+    lt_pf_slice(P, pf_i++, pf_slices);
     lt_gemm_phase<-1, ST, SB>(P.g_w2, &tmFfn, &tmW2, P.has_qkv ? &P.g_qkv : nullptr, &tmWqkv, P, P.ffn, ring, sm, tmem_acc, g, acc_uses, 20);
     LT_TS(8);
-    lt_grid_barrier(P.bar, bar_target);
+    lt_grid_barrier(P.bar, bar_target, P.err);
     LT_TS(9);
+    lt_pf_slice(P, pf_i++, pf_slices);
     lt_norm_phase(&P.g_w2, P.norm2_w, P, sm);
     LT_TS(10);
   } else {
+    lt_pf_slice(P, pf_i++, pf_slices);
     lt_norm_phase(nullptr, P.norm2_w, P, sm);
   }
   if (P.has_qkv) {
-    lt_grid_barrier(P.bar, bar_target);
+    lt_grid_barrier(P.bar, bar_target, P.err);
     LT_TS(11);
+    lt_pf_slice(P, pf_i++, pf_slices);
     lt_gemm_phase<EPI_QKV_ROPE, ST, SB>(P.g_qkv, &tmXn, &tmWqkv, nullptr, nullptr, P, P.rope, ring, sm, tmem_acc, g, acc_uses, 22);
     LT_TS(12);
   }
@@ -445,6 +535,8 @@ layer_tail_kernel(const __grid_constant__ TensorMap tmAttn, const __grid_constan
 static bool lt_pick(int N, int K, int sms, bool split, LtGemm* out) {
   if (K % 64 != 0 || N % 64 != 0) return false;
   const int nkb = K / 64;
+  // split count cap: the row phase that reduces the partials keeps 8 loads per thread in flight per L2 round trip
+  static const int max_s = [] { const char* e = getenv("VLG_LT_MAXS"); return e ? atoi(e) : 8; }();
   double best = 1e30;
   bool found = false;
   const int bns[3] = {32, 64, 128};
@@ -454,6 +546,7 @@ static bool lt_pick(int N, int K, int sms, bool split, LtGemm* out) {
     if (tiles > sms) continue;
     int s0 = split ? sms / tiles : 1;
     if (s0 > nkb) s0 = nkb;
+    if (s0 > max_s) s0 = max_s;
     const int kb_per = (nkb + s0 - 1) / s0;
     const int S = (nkb + kb_per - 1) / kb_per;
     // costed at the full 128-row tile so that the choice (and the scratch size) does not depend on the batch
@@ -516,8 +609,22 @@ int launch_layer_tail(const LtLaunch& a, cudaStream_t st) {
   P.ffn.out = a.ffn; P.ffn.ld_out = a.hidden;
   P.rope = a.rope;
   P.bar = a.bar;
+  P.err = a.err;
   static const int dbg = [] { const char* e = getenv("VLG_LT_DEBUG"); return e ? atoi(e) : 0; }();
   P.dbg = dbg;
+  static const int fast_silu = [] { const char* e = getenv("VLG_LT_FASTSILU"); return e ? atoi(e) : 1; }();
+  P.fast_silu = fast_silu;
+  // L2 prefetch budget per launch (MB of next-layer K + V).  OFF by default: measured on B200 (gpurun_out of round 2,
+  // DESIGN.md 4.1) the attention kernel runs at the same speed from L2-resident K/V as from HBM (its shared-memory / issue
+  // side bounds it at ~7.9 TB/s), while the fill traffic adds latency to every phase of this kernel: 819 / 846 / 902 / 954 ms
+  // per cfg-2 generate at 0 / 48 / 80 / 112 MB.  VLG_KV_PREFETCH_MB=<n> re-enables it for A/B runs.
+  static const long long pf_mb = [] { const char* e = getenv("VLG_KV_PREFETCH_MB"); return e ? atoll(e) : 0LL; }();
+  if (pf_mb > 0 && a.pf_k != nullptr && a.pf_v != nullptr && a.pf_n_rh > 0) {
+    P.pf_k = static_cast<const uint8_t*>(a.pf_k); P.pf_v = static_cast<const uint8_t*>(a.pf_v);
+    P.pf_n_rh = a.pf_n_rh; P.pf_stride = a.pf_stride_bytes; P.pf_pos_ptr = a.pf_pos_ptr; P.pf_pos_imm = a.pf_pos_imm;
+    P.pf_budget = pf_mb << 20;
+  }
+  if (pf_mb > 0 && a.pf_flat != nullptr) { P.pf_flat = static_cast<const uint8_t*>(a.pf_flat); P.pf_flat_bytes = (long long)a.pf_flat_bytes; }
 
   TensorMap tmAttn{}, tmXn{}, tmFfn{}, tmWo{}, tmW13{}, tmW2{}, tmWqkv{};
   int rc;
@@ -536,11 +643,8 @@ int launch_layer_tail(const LtLaunch& a, cudaStream_t st) {
   const bool narrow = P.g_wo.BN <= 64 && P.g_w13.BN <= 64 && P.g_w2.BN <= 64 && P.g_qkv.BN <= 64;
   auto kern = narrow ? layer_tail_kernel<kLtStagesNarrow, kLtStageBytesNarrow> : layer_tail_kernel<kLtStages, kLtStageBytesWide>;
   const int smem = narrow ? lt_smem_bytes(kLtStagesNarrow, kLtStageBytesNarrow) : lt_smem_bytes(kLtStages, kLtStageBytesWide);
-  static bool attr_set[2] = {false, false};
-  if (!attr_set[narrow]) {
-    VLG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_set[narrow] = true;
-  }
+  static PerDeviceOnce attr_once[2];
+  VLG_CUDA(attr_once[narrow]([&] { return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); }));
   VLG_CUDA(launch_kernel(kern, dim3(sms), dim3(kLtThreads), (size_t)smem, st, tmAttn, tmXn, tmFfn, tmWo, tmW13, tmW2, tmWqkv, P));
   VLG_LAUNCH_CHECK();
   return VLG_OK;

@@ -217,7 +217,8 @@ __global__ void __launch_bounds__(kSampThreads, 1) cfg_sample_kernel(SampleArgs 
   }
 
   // ---- 5. pick
-  const uint2 pkey = make_uint2((uint32_t)a.p.seed, (uint32_t)(a.p.seed >> 32));
+  const unsigned long long seed = a.seed_ptr ? *a.seed_ptr : (unsigned long long)a.p.seed;
+  const uint2 pkey = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
   const uint64_t off = a.p.offset + (uint64_t)step;
   float best = -INFINITY;
   int besti = 0x7fffffff;
@@ -302,10 +303,11 @@ int launch_sample(const SampleArgs& a, cudaStream_t st) {
   }
   VLG_REQUIRE(smem <= 220 * 1024, "sample: vocabulary %d too large for the shared-memory sampler%s", a.V,
               a.p.top_p < 1.0f ? " with top-p" : "");
-  static size_t attr = 0;
-  if (smem > attr) {
+  static size_t attr[kMaxDevices] = {};
+  const int dev = current_device();
+  if (smem > attr[dev]) {
     VLG_CUDA(cudaFuncSetAttribute(cfg_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = smem;
+    attr[dev] = smem;
   }
   VLG_CUDA(launch_kernel(cfg_sample_kernel, dim3(a.B), dim3(kSampThreads), smem, st, a));
   VLG_LAUNCH_CHECK();

@@ -9,14 +9,16 @@
 // Exactness: d is formed with the reference's rounding sequence -- (|z|^2 + |e|^2) rounded, then
 // minus 2*dot rounded (fma(-2, dot, s) is that exactly, doubling being exact) -- and ties keep the
 // lowest index, like torch.argmin.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace vlg {
 
-// normalise the codebook rows and precompute |e_j|^2 (F.normalize eps = 1e-12, vq_model.py:224)
+// normalise the codebook rows and precompute |e_j|^2 (F.normalize eps = 1e-12, vq_model.py:224); *e2max = max_j |e_j|^2
 template <int C>
 __global__ void vq_prep_kernel(const float* __restrict__ cb, float* __restrict__ en, float* __restrict__ e2, int n_e,
-                               int l2_norm) {
+                               int l2_norm, float* __restrict__ e2max) {
   int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n_e) return;
   float e[C];
@@ -37,8 +39,220 @@ __global__ void vq_prep_kernel(const float* __restrict__ cb, float* __restrict__
     en[(size_t)j * C + c] = e[c];
   }
   e2[j] = s2;
+  if (e2max) atomicMax(reinterpret_cast<int*>(e2max), __float_as_int(s2));   // s2 >= 0: int order == float order
 }
 
+
+// ---------------------------------------------------------------------------------------------- fast path (cfg-5 shape)
+// The exact kernel below spends 13 issue slots per (latent, code) pair -- 8 for the dot product, 5 for the reference's
+// d = (|z|^2 + |e|^2) - 2 z.e and the running argmin -- and the FP32 pipe sees 10 of them.  This kernel does the dot
+// products alone, two latents per instruction (fma.rn.f32x2 -> FFMA2), in the score domain
+//     s_j = z.e_j - |e_j|^2 / 2        (argmax_j s_j == argmin_j d_j in exact arithmetic),
+// keeps, per latent, the best score / its index / the runner-up score (a 3-input max per two codes, the index only on the
+// rare new record), and proves the result instead of trusting it: the reference's fp32 evaluation of d_j can disagree with
+// the score order only where two scores are closer than the rounding noise of both formulas, so a latent whose runner-up
+// is within `eps` of its best (about 3 in 10 000 at cfg-5) is re-done by vq_recheck_kernel with the reference's rounding
+// sequence over all codes (same arithmetic as vq_argmin_kernel: bit-identical indices by construction).
+//   noise budget (unit-norm rows, |z| = |e| = 1): reference d_j: ulp(2)/2 + ulp(d)/2 + 2 * 8-term dot error <= 1.3e-6,
+//   scores: 8-term fma chain <= 5e-7 each; eps = 4e-6 * (|z| + |e|max)^2 covers twice their sum.
+constexpr int kVq2Threads = 128;
+constexpr int kVq2Chunk = 1024;    // codes per shared-memory fill: 1024 * (8 dims * 2 copies + 2) * 4 B = 72 KB
+constexpr int kVq2Group = 8;       // codes whose scores stay in registers between index look-ups
+
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
+  return (unsigned long long)__float_as_uint(lo) | ((unsigned long long)__float_as_uint(hi) << 32);
+}
+__device__ __forceinline__ unsigned long long ffma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ float lo32(unsigned long long v) { return __uint_as_float((unsigned)v); }
+__device__ __forceinline__ float hi32(unsigned long long v) { return __uint_as_float((unsigned)(v >> 32)); }
+__device__ __forceinline__ float max3f(float a, float b, float c) {
+  float r;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
+
+// LP latent pairs per thread (2 * LP latents), C = 8 only.
+template <int LP>
+__global__ void __launch_bounds__(kVq2Threads)
+vq_score_kernel(const float* __restrict__ z, const float* __restrict__ en, const float* __restrict__ e2,
+                const float* __restrict__ e2max, int64_t* __restrict__ idx_out, float* __restrict__ zq,
+                unsigned* __restrict__ amb_count, int* __restrict__ amb_list, int64_t N, int64_t HW, int n_e, int l2_norm) {
+  constexpr int C = 8, L = 2 * LP;
+  extern __shared__ __align__(16) float sm[];
+  float* s_e = sm;                          // [chunk][C][2]: every component twice, so one 64-bit load feeds both halves of an FFMA2
+  float* s_h = sm + kVq2Chunk * C * 2;      // [chunk][2]:   -|e_j|^2 / 2, twice
+
+  const int64_t base = (int64_t)blockIdx.x * (kVq2Threads * L) + threadIdx.x;
+  unsigned long long zp[LP][C];             // latent pair p = latents (base + (2p) * T, base + (2p+1) * T)
+  float zraw[L][C];
+  float z2[L];
+#pragma unroll
+  for (int l = 0; l < L; ++l) {
+    const int64_t n = base + (int64_t)l * kVq2Threads;
+    const bool ok = n < N;
+    const int64_t b = ok ? n / HW : 0, hw = ok ? n % HW : 0;
+    float ss = 0.f;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      zraw[l][c] = ok ? z[(b * C + c) * HW + hw] : 0.f;
+      ss = __fadd_rn(ss, __fmul_rn(zraw[l][c], zraw[l][c]));
+    }
+    if (l2_norm) {
+      const float nrm = fmaxf(sqrtf(ss), 1e-12f);
+      ss = 0.f;
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        zraw[l][c] = __fdiv_rn(zraw[l][c], nrm);
+        ss = __fadd_rn(ss, __fmul_rn(zraw[l][c], zraw[l][c]));
+      }
+    }
+    z2[l] = ss;
+  }
+#pragma unroll
+  for (int p = 0; p < LP; ++p)
+#pragma unroll
+    for (int c = 0; c < C; ++c) zp[p][c] = pack2(zraw[2 * p][c], zraw[2 * p + 1][c]);
+
+  float best[L], second[L];
+  int bidx[L];
+#pragma unroll
+  for (int l = 0; l < L; ++l) { best[l] = -INFINITY; second[l] = -INFINITY; bidx[l] = 0; }
+
+  for (int c0 = 0; c0 < n_e; c0 += kVq2Chunk) {
+    const int cn = min(kVq2Chunk, n_e - c0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < cn * C; i += kVq2Threads) {
+      const float v = en[(size_t)c0 * C + i];
+      reinterpret_cast<float2*>(s_e)[i] = make_float2(v, v);
+    }
+    for (int i = threadIdx.x; i < kVq2Chunk; i += kVq2Threads) {
+      const float h = i < cn ? -0.5f * e2[c0 + i] : -INFINITY;        // padding codes can never win
+      reinterpret_cast<float2*>(s_h)[i] = make_float2(h, h);
+    }
+    if (cn < kVq2Chunk)
+      for (int i = cn * C + threadIdx.x; i < kVq2Chunk * C; i += kVq2Threads) reinterpret_cast<float2*>(s_e)[i] = make_float2(0.f, 0.f);
+    __syncthreads();
+    for (int j0 = 0; j0 < kVq2Chunk; j0 += kVq2Group) {
+      unsigned long long sc[LP][kVq2Group];
+#pragma unroll
+      for (int j = 0; j < kVq2Group; ++j) {
+        const ulonglong2* ep = reinterpret_cast<const ulonglong2*>(s_e + (size_t)(j0 + j) * C * 2);   // warp-wide broadcasts
+        const ulonglong2 e01 = ep[0], e23 = ep[1], e45 = ep[2], e67 = ep[3];
+        const unsigned long long h = reinterpret_cast<const unsigned long long*>(s_h)[j0 + j];
+#pragma unroll
+        for (int p = 0; p < LP; ++p) {
+          unsigned long long a = ffma2(zp[p][0], e01.x, h);
+          a = ffma2(zp[p][1], e01.y, a);
+          a = ffma2(zp[p][2], e23.x, a);
+          a = ffma2(zp[p][3], e23.y, a);
+          a = ffma2(zp[p][4], e45.x, a);
+          a = ffma2(zp[p][5], e45.y, a);
+          a = ffma2(zp[p][6], e67.x, a);
+          sc[p][j] = ffma2(zp[p][7], e67.y, a);
+        }
+      }
+#pragma unroll
+      for (int l = 0; l < L; ++l) {
+        float s[kVq2Group];
+#pragma unroll
+        for (int j = 0; j < kVq2Group; ++j) s[j] = (l & 1) ? hi32(sc[l >> 1][j]) : lo32(sc[l >> 1][j]);
+        const float m = max3f(max3f(s[0], s[1], s[2]), max3f(s[3], s[4], s[5]), fmaxf(s[6], s[7]));
+        if (m > best[l]) {                   // new record (rare: ~ln(n_e) times per latent): find it, demote the old best
+          float run = second[l] > best[l] ? second[l] : best[l];
+          int arg = -1;
+#pragma unroll
+          for (int j = 0; j < kVq2Group; ++j) {
+            if (arg < 0 && s[j] == m) arg = j;                 // first index among equals
+            else run = fmaxf(run, s[j]);
+          }
+          second[l] = run;
+          best[l] = m;
+          bidx[l] = c0 + j0 + arg;
+        } else {
+          second[l] = fmaxf(second[l], m);
+        }
+      }
+    }
+  }
+
+  const float emax = e2max ? *e2max : 1.f;
+#pragma unroll
+  for (int l = 0; l < L; ++l) {
+    const int64_t n = base + (int64_t)l * kVq2Threads;
+    if (n >= N) continue;
+    const float mag = sqrtf(z2[l]) + sqrtf(emax);
+    const float eps = 4e-6f * fmaxf(mag * mag, 1e-30f);
+    if (!(best[l] - second[l] > eps)) {      // runner-up inside the rounding noise (or NaN scores): settle it exactly
+      const unsigned slot = atomicAdd(amb_count, 1u);
+      amb_list[slot] = (int)n;               // amb_list holds N entries: cannot overflow
+      continue;
+    }
+    idx_out[n] = bidx[l];
+    if (zq) {
+      const int64_t b = n / HW, hw = n % HW;
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        const float e = en[(size_t)bidx[l] * C + c];
+        zq[(b * C + c) * HW + hw] = __fadd_rn(zraw[l][c], __fsub_rn(e, zraw[l][c]));
+      }
+    }
+  }
+}
+
+// One warp per ambiguous latent: the reference's rounding sequence for d over all codes (same arithmetic as
+// vq_argmin_kernel), lanes stride the codebook, minimum with the lowest index on ties.
+template <int C>
+__global__ void __launch_bounds__(256)
+vq_recheck_kernel(const float* __restrict__ z, const float* __restrict__ en, const float* __restrict__ e2,
+                  int64_t* __restrict__ idx_out, float* __restrict__ zq, const unsigned* __restrict__ amb_count,
+                  const int* __restrict__ amb_list, int64_t HW, int n_e, int l2_norm) {
+  const int lane = threadIdx.x & 31;
+  const unsigned total = *amb_count;
+  for (unsigned w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); w < total; w += gridDim.x * (blockDim.x >> 5)) {
+    const int64_t n = amb_list[w];
+    const int64_t b = n / HW, hw = n % HW;
+    float zr[C];
+    float ss = 0.f;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      zr[c] = z[(b * C + c) * HW + hw];
+      ss = __fadd_rn(ss, __fmul_rn(zr[c], zr[c]));
+    }
+    if (l2_norm) {
+      const float nrm = fmaxf(sqrtf(ss), 1e-12f);
+      ss = 0.f;
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        zr[c] = __fdiv_rn(zr[c], nrm);
+        ss = __fadd_rn(ss, __fmul_rn(zr[c], zr[c]));
+      }
+    }
+    float best = INFINITY;
+    int bi = 0x7fffffff;
+    for (int j = lane; j < n_e; j += 32) {
+      float dot = __fmul_rn(zr[0], en[(size_t)j * C]);
+#pragma unroll
+      for (int c = 1; c < C; ++c) dot = __fmaf_rn(zr[c], en[(size_t)j * C + c], dot);
+      const float d = __fmaf_rn(-2.f, dot, __fadd_rn(ss, e2[j]));
+      if (d < best) { best = d; bi = j; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ob < best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+    }
+    if (bi == 0x7fffffff) bi = 0;            // all-NaN row: torch.argmin would return the first NaN; index 0 here
+    if (lane == 0) idx_out[n] = bi;
+    if (zq && lane < C) zq[(b * C + lane) * HW + hw] = __fadd_rn(zr[lane], __fsub_rn(en[(size_t)bi * C + lane], zr[lane]));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- exact kernel (any C)
 constexpr int kVqThreads = 256;
 constexpr int kVqChunk = 2048;  // codes staged per shared-memory fill
 
@@ -151,12 +365,52 @@ __global__ void codebook_gather_kernel(const int64_t* __restrict__ idx, const fl
   }
 }
 
+// get_codebook_entry + post_quant_conv (1x1): one thread per latent position holds its normalised code in registers and
+// walks the O output channels; the [O, C] weight and the bias sit in shared memory and are read as warp broadcasts, the
+// stores are coalesced along hw.  HBM-bound on the [B, O, HW] write.
+template <int C>
+__global__ void __launch_bounds__(128)
+codebook_project_kernel(const int64_t* __restrict__ idx, const float* __restrict__ cb, const float* __restrict__ w,
+                        const float* __restrict__ bias, float* __restrict__ out, int64_t N, int64_t HW, int n_e, int O,
+                        int l2_norm) {
+  extern __shared__ __align__(16) float sm[];
+  float* s_w = sm;            // [O][C]
+  float* s_b = sm + O * C;    // [O]
+  for (int i = threadIdx.x; i < O * C; i += blockDim.x) s_w[i] = w[i];
+  for (int i = threadIdx.x; i < O; i += blockDim.x) s_b[i] = bias ? bias[i] : 0.f;
+  __syncthreads();
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  int64_t j = idx[n];
+  if (j < 0 || j >= n_e) j = 0;
+  float e[C];
+  float ss = 0.f;
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    e[c] = cb[j * C + c];
+    ss = __fadd_rn(ss, __fmul_rn(e[c], e[c]));
+  }
+  if (l2_norm) {
+    const float nrm = fmaxf(sqrtf(ss), 1e-12f);
+#pragma unroll
+    for (int c = 0; c < C; ++c) e[c] = __fdiv_rn(e[c], nrm);
+  }
+  const int64_t b = n / HW, hw = n - b * HW;
+  float* dst = out + b * O * HW + hw;
+  for (int o = 0; o < O; ++o) {
+    float acc = s_b[o];
+#pragma unroll
+    for (int c = 0; c < C; ++c) acc = __fmaf_rn(s_w[o * C + c], e[c], acc);
+    dst[(int64_t)o * HW] = acc;
+  }
+}
+
 template <int C, int L>
 static int launch_vq(const float* z, const float* cb, int64_t* idx, float* zq, float* scratch, int64_t N, int64_t HW,
                      int n_e, int l2_norm, cudaStream_t st) {
   float* en = scratch;
   float* e2 = scratch + (size_t)n_e * C;
-  vq_prep_kernel<C><<<(n_e + 255) / 256, 256, 0, st>>>(cb, en, e2, n_e, l2_norm);
+  vq_prep_kernel<C><<<(n_e + 255) / 256, 256, 0, st>>>(cb, en, e2, n_e, l2_norm, nullptr);
   VLG_LAUNCH_CHECK();
   size_t smem = (size_t)kVqChunk * (C + 1) * sizeof(float);
   auto kern = vq_argmin_kernel<C, L>;
@@ -170,6 +424,37 @@ static int launch_vq(const float* z, const float* cb, int64_t* idx, float* zq, f
 
 }  // namespace vlg
 
+namespace vlg {
+// C = 8 with the work area of vlg_vq_scratch_floats(): score-domain FFMA2 kernel + exact recheck of the ambiguous latents
+static int launch_vq_fast(const float* z, const float* cb, int64_t* idx, float* zq, float* scratch, int64_t N, int64_t HW,
+                          int n_e, int l2_norm, cudaStream_t st) {
+  constexpr int C = 8, LP = 4;
+  float* en = scratch;
+  float* e2 = scratch + (size_t)n_e * C;
+  float* e2max = e2 + n_e;                                         // 1 float
+  unsigned* amb_count = reinterpret_cast<unsigned*>(e2max + 1);    // 1 word
+  int* amb_list = reinterpret_cast<int*>(e2max + 2);               // N words
+  VLG_CUDA(cudaMemsetAsync(e2max, 0, 2 * sizeof(float), st));
+  vq_prep_kernel<C><<<(n_e + 255) / 256, 256, 0, st>>>(cb, en, e2, n_e, l2_norm, e2max);
+  VLG_LAUNCH_CHECK();
+  const size_t smem = (size_t)kVq2Chunk * (C * 2 + 2) * sizeof(float);
+  auto kern = vq_score_kernel<LP>;
+  static PerDeviceOnce once;
+  VLG_CUDA(once([&] { return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); }));
+  const int64_t per_block = (int64_t)kVq2Threads * 2 * LP;
+  kern<<<(unsigned)((N + per_block - 1) / per_block), kVq2Threads, smem, st>>>(z, en, e2, e2max, idx, zq, amb_count, amb_list, N,
+                                                                               HW, n_e, l2_norm);
+  VLG_LAUNCH_CHECK();
+  vq_recheck_kernel<C><<<num_sms() * 2, 256, 0, st>>>(z, en, e2, idx, zq, amb_count, amb_list, HW, n_e, l2_norm);
+  VLG_LAUNCH_CHECK();
+  return VLG_OK;
+}
+}  // namespace vlg
+
+extern "C" size_t vlg_vq_scratch_floats(int64_t N, int C, int n_e) {
+  return (size_t)n_e * (C + 1) + 2 + (size_t)(N > 0 ? N : 0);
+}
+
 extern "C" int vlg_vq_argmin(const float* z_dev, const float* codebook_dev, int64_t* idx_dev, float* zq_dev,
                              float* scratch_dev, int64_t B, int C, int64_t HW, int n_e, int l2_norm, void* stream) {
   using namespace vlg;
@@ -180,6 +465,8 @@ extern "C" int vlg_vq_argmin(const float* z_dev, const float* codebook_dev, int6
   VLG_REQUIRE(z_dev && codebook_dev && idx_dev && scratch_dev, "vlg_vq_argmin: null pointer");
   VLG_REQUIRE(N / ((int64_t)kVqThreads) < (1ll << 31), "vlg_vq_argmin: too many latents");
   cudaStream_t st = (cudaStream_t)stream;
+  static const bool exact_only = [] { const char* e = getenv("VLG_VQ_EXACT"); return e && e[0] == '1'; }();   // A/B switch
+  if (C == 8 && !exact_only && N < (1ll << 31)) return launch_vq_fast(z_dev, codebook_dev, idx_dev, zq_dev, scratch_dev, N, HW, n_e, l2_norm, st);
   switch (C) {
     case 4: return launch_vq<4, 4>(z_dev, codebook_dev, idx_dev, zq_dev, scratch_dev, N, HW, n_e, l2_norm, st);
     case 8: return launch_vq<8, 4>(z_dev, codebook_dev, idx_dev, zq_dev, scratch_dev, N, HW, n_e, l2_norm, st);
@@ -209,5 +496,75 @@ extern "C" int vlg_codebook_gather(const int64_t* idx_dev, const float* codebook
       return VLG_ERR_ARG;
   }
   VLG_LAUNCH_CHECK();
+  return VLG_OK;
+}
+
+extern "C" int vlg_codebook_project(const int64_t* idx_dev, const float* codebook_dev, const float* weight_dev,
+                                    const float* bias_dev, float* out_dev, int64_t B, int C, int64_t HW, int n_e, int O,
+                                    int l2_norm, void* stream) {
+  using namespace vlg;
+  const int64_t N = B * HW;
+  if (N == 0) return VLG_OK;
+  VLG_REQUIRE(idx_dev && codebook_dev && weight_dev && out_dev, "vlg_codebook_project: null pointer");
+  VLG_REQUIRE(O > 0 && (size_t)O * (C + 1) * sizeof(float) <= 48 * 1024, "vlg_codebook_project: %d output channels do not fit shared memory", O);
+  cudaStream_t st = (cudaStream_t)stream;
+  const unsigned blocks = (unsigned)((N + 127) / 128);
+  const size_t smem = (size_t)O * (C + 1) * sizeof(float);
+  switch (C) {
+    case 4: codebook_project_kernel<4><<<blocks, 128, smem, st>>>(idx_dev, codebook_dev, weight_dev, bias_dev, out_dev, N, HW, n_e, O, l2_norm); break;
+    case 8: codebook_project_kernel<8><<<blocks, 128, smem, st>>>(idx_dev, codebook_dev, weight_dev, bias_dev, out_dev, N, HW, n_e, O, l2_norm); break;
+    case 16: codebook_project_kernel<16><<<blocks, 128, smem, st>>>(idx_dev, codebook_dev, weight_dev, bias_dev, out_dev, N, HW, n_e, O, l2_norm); break;
+    case 32: codebook_project_kernel<32><<<blocks, 128, smem, st>>>(idx_dev, codebook_dev, weight_dev, bias_dev, out_dev, N, HW, n_e, O, l2_norm); break;
+    default:
+      set_error("vlg_codebook_project: codebook_embed_dim %d not supported (4, 8, 16, 32)", C);
+      return VLG_ERR_ARG;
+  }
+  VLG_LAUNCH_CHECK();
+  return VLG_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- FP32 roofline probe
+// Register-resident FMA loop (the VQ index search is bounded by the FP32 pipe, so its roofline denominator is
+// measured on the box, not quoted): 8 independent accumulator chains per thread, 2 CTAs of 512 threads per SM.
+// variant 0: scalar FFMA, variant 1: packed FFMA2 (fma.rn.f32x2).  flops = grid * 512 * iters * 16 * (variant ? 2 : 1).
+namespace vlg {
+template <int X2>
+__global__ void __launch_bounds__(512) fp32_peak_kernel(float* out, int iters, float a, float b) {
+  if (X2) {
+    unsigned long long acc[8], av = pack2(a, a), bv = pack2(b, b);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = pack2((float)threadIdx.x + i, (float)i);
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] = ffma2(acc[i], av, bv);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += lo32(acc[i]) + hi32(acc[i]);
+    if (s == 12345.678f) out[0] = s;
+  } else {
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = (float)threadIdx.x + i;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] = __fmaf_rn(acc[i], a, b);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += acc[i];
+    if (s == 12345.678f) out[0] = s;
+  }
+}
+}  // namespace vlg
+
+extern "C" int vlg_debug_fp32_fma_peak(int variant, int iters, float* out_dev, long long* flops_out, void* stream) {
+  using namespace vlg;
+  VLG_REQUIRE(out_dev && iters > 0, "vlg_debug_fp32_fma_peak: bad arguments");
+  const int grid = num_sms() * 2;
+  if (variant) fp32_peak_kernel<1><<<grid, 512, 0, (cudaStream_t)stream>>>(out_dev, iters, 0.999f, 0.001f);
+  else fp32_peak_kernel<0><<<grid, 512, 0, (cudaStream_t)stream>>>(out_dev, iters, 0.999f, 0.001f);
+  VLG_LAUNCH_CHECK();
+  if (flops_out) *flops_out = (long long)grid * 512 * iters * 16 * (variant ? 2 : 1);
   return VLG_OK;
 }

@@ -45,13 +45,16 @@ SIGNATURES = {
     "vlg_abi_version": (_I, []),
     "vlg_last_error": (C.c_char_p, []),
     "vlg_launch_count": (C.c_uint64, []),
+    "vlg_vq_scratch_floats": (_SZ, [_I64, _I, _I]),
     "vlg_vq_argmin": (_I, [_P, _P, _P, _P, _P, _I64, _I, _I64, _I, _I, _P]),
     "vlg_codebook_gather": (_I, [_P, _P, _P, _I64, _I, _I64, _I, _I, _I, _P]),
+    "vlg_codebook_project": (_I, [_P, _P, _P, _P, _P, _I64, _I, _I64, _I, _I, _I, _P]),
     "vlg_cfg_sample": (_I, [_P, _I, _I, _I, C.POINTER(SampleParams), _P, _P, _P, _P]),
     "vlg_top_k_top_p": (_I, [_P, _P, _I, _I, _I, _F, _P]),
     "vlg_ctx_workspace_bytes": (_SZ, [C.POINTER(Geometry), _I, _I]),
     "vlg_ctx_create": (_I, [C.POINTER(Geometry), C.POINTER(Weights), _I, _I, _P, _SZ, C.POINTER(_P)]),
     "vlg_ctx_destroy": (None, [_P]),
+    "vlg_ctx_check": (_I, [_P, _P]),
     "vlg_begin": (_I, [_P, _I, _P, _P]),
     "vlg_forward_pos": (_I, [_P, _P, _P, _P, _I, _P, _P, _P]),
     "vlg_mlp": (_I, [_P, _I, _P, _P, _I, _P]),
@@ -62,6 +65,7 @@ SIGNATURES = {
     "vlg_linear": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "vlg_attn_decode": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _I, _I, _I, _P, _SZ, _P]),
     "vlg_attn_scratch_bytes": (_SZ, [_I, _I, _I, _I]),
+    "vlg_debug_fp32_fma_peak": (_I, [_I, _I, _P, C.POINTER(C.c_longlong), _P]),
     "vlg_debug_gemm_timestamps": (_I, [_P]),
     "vlg_debug_lt_timestamps": (_I, [_P]),
     "vlg_debug_trunk_without_attention": (_I, [_P, _I, _P]),

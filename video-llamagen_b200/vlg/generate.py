@@ -22,11 +22,14 @@ def _seed(device):
 
 
 def _run_sampler(logits2d, rows, B, cfg_scale, guided, temperature, top_k, top_p, sample_logits, noise=None,
-                 want_probs=True, seed=None):
+                 want_probs=True, seed=None, offset=0):
+    """One launch of the fused sampler.  ``want_probs=False`` with ``noise=None`` and ``sample_logits=True`` selects the
+    kernel branch the in-library decode loop runs (no probability write, Philox draws, log-domain race); ``offset`` is
+    the Philox stream offset the loop derives from the step index."""
     L.require_cuda(logits2d, "sample")
     V = logits2d.shape[-1]
     p = L.SampleParams(float(cfg_scale), int(guided), float(temperature), int(top_k or 0), float(top_p),
-                       int(bool(sample_logits)), int(seed if seed is not None else _seed(logits2d.device)), 0)
+                       int(bool(sample_logits)), int(seed if seed is not None else _seed(logits2d.device)), int(offset))
     idx = torch.empty(B, dtype=torch.int64, device=logits2d.device)
     probs = torch.empty(B, V, dtype=torch.float32, device=logits2d.device) if want_probs else None
     if noise is not None:

@@ -224,6 +224,11 @@ class Engine:
         except Exception:
             pass
 
+    def check(self):
+        """Synchronise and raise if a decode launch since the last check lost its SMs to other work (vlg_ctx_check)."""
+        with torch.cuda.device(self.device):
+            L.check(L.lib().vlg_ctx_check(self.ctx, L.stream()))
+
     def begin(self, rows, prefix_mask=None):
         m = None
         if prefix_mask is not None:
