@@ -217,11 +217,15 @@ def test_gptxxl_cfg3_full_depth_shard_bf16():
         x = torch.cat([toks[:, i:i + 1], toks[:, i:i + 1]])
         out.append(m(x, None, torch.tensor([1 + i], device=DEV))[0][:, -1])
     ours = torch.stack(out).float()
-    scale = max(1.0, truth.pow(2).mean().sqrt().item() / 0.55)
-    assert torch.allclose(ours, ref, rtol=BF16_RTOL, atol=BF16_ATOL * scale), ((ours - ref).abs().max(), scale)
     rms_ours = (ours - truth).pow(2).mean().sqrt().item()
     rms_ref = (ref - truth).pow(2).mean().sqrt().item()
-    assert rms_ours <= 1.5 * rms_ref + 1e-4, (rms_ours, rms_ref)
+    assert rms_ours <= 1.5 * rms_ref + 1e-4, (rms_ours, rms_ref)       # no noisier than the reference's own bf16 run
+    # Elementwise gate.  SURVEY 8c calibrated atol 0.06 (at logit rms 0.55) on a 12-layer model; bf16 rounding noise grows
+    # with depth, so at 48 layers the floor is taken from the reference itself: two independent bf16 evaluations differ by
+    # sqrt(2) x its rms error per element, and the largest of these 9.4 M elements sits ~5.3 sigma out -> 10 x rms_ref.
+    scale = max(1.0, truth.pow(2).mean().sqrt().item() / 0.55)
+    atol = max(BF16_ATOL * scale, 10.0 * rms_ref)
+    assert torch.allclose(ours, ref, rtol=BF16_RTOL, atol=atol), ((ours - ref).abs().max(), atol, rms_ours, rms_ref)
 
 
 def test_t2v_tiny_trunk_adapters_3d_rope(golden):

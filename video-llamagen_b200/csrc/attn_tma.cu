@@ -12,6 +12,8 @@
 //     position for p.V; per-warp partial (m, l, o) states are merged through shared memory once per item.
 // Numerics: fp32 throughout, single rounding of the output to bf16 (torch math SDPA);
 // the softmax scale is folded into q (1/sqrt(D) is a power of two for D = 64) together with log2(e).
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -375,14 +377,24 @@ int launch_attn_tma(int dtype, const AttnArgs& a, cudaStream_t st) {
   if (rc) return rc;
   if ((rc = make_tmap_bf16_2d(&tmV, a.v_cache, total_rows, 64, 128, kTile, 64, true))) return rc;
 
-  // sequence splits only when (row, head) pairs alone cannot occupy the SMs
+  // Sequence splits: a small cost model over the position mix of the run (mean prefix = half of max_pos, since a captured
+  // graph fixes the split count for every step).  One CTA streams ~53 GB/s (measured: the kernel is bound by its
+  // shared-memory / issue side at 7.9 TB/s over 148 SMs), an item costs ~0.3 us of fixed work, and any split count > 1
+  // pays for the combine launch (~3.5 us with its kernel boundary) -- so e.g. 256 (row, head) pairs on 148 SMs stay
+  // unsplit (two rounds of whole items beat four rounds of half items plus a combine), while 40 long pairs split 7-fold.
   const int sms = num_sms();
   int n_splits = 1;
-  if (n_rh < 2 * sms) {
-    int want = (2 * sms + n_rh - 1) / n_rh, by_len = (a.max_pos + 1 + 2 * kTile - 1) / (2 * kTile);
-    n_splits = want < by_len ? want : by_len;
-    if (n_splits < 1) n_splits = 1;
-    if (n_splits > kMaxSplitsT) n_splits = kMaxSplitsT;
+  {
+    const double item_us = 0.5 * (a.max_pos + 1) * 256.0 / 53e3, fixed_us = 0.3, combine_us = 3.5;
+    double best = 1e30;
+    const int max_s = (a.max_pos + 1 + kTile - 1) / kTile < kMaxSplitsT ? (a.max_pos + 1 + kTile - 1) / kTile : kMaxSplitsT;
+    for (int sp = 1; sp <= (max_s < 1 ? 1 : max_s); ++sp) {
+      const double rounds = (double)(((long)n_rh * sp + sms - 1) / sms);
+      const double t = rounds * (item_us / sp + fixed_us) + (sp > 1 ? combine_us : 0.0);
+      if (t < best - 1e-9) { best = t; n_splits = sp; }
+    }
+    static const int force = [] { const char* e = getenv("VLG_ATTN_SPLITS"); return e ? atoi(e) : 0; }();   // A/B
+    if (force > 0) n_splits = force > max_s ? (max_s < 1 ? 1 : max_s) : force;
   }
   if (n_splits > 1)
     VLG_REQUIRE(a.scratch && a.scratch_bytes >= (size_t)n_rh * n_splits * 66 * sizeof(float),

@@ -85,7 +85,7 @@ __device__ __forceinline__ void fused_rmsnorm_row(const __nv_bfloat16* __restric
 template <int BM, int BN, int EPI>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_tc_kernel(const __grid_constant__ TensorMap tmA, const __grid_constant__ TensorMap tmB, int rows, int K,
-                    EpiParams P, int dbg) {
+                    EpiParams P, int dbg, uint32_t a_bytes) {
   using Cfg = GemmCfg<BM, BN>;
   extern __shared__ uint8_t smem_raw[];
   __shared__ float s_norm_part[4];
@@ -121,7 +121,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ TensorMap tmA, const __grid_constant
       // waiting for its output, so the weight stream overlaps the predecessor's tail.
       const int pre = nkb < Cfg::kStages ? nkb : Cfg::kStages;
       // dbg (microbenchmarks only): bit 0 skips the activation loads, bit 1 the weight loads
-      const uint32_t tx = ((dbg & 1) ? 0 : BM * kBK * 2) + ((dbg & 2) ? 0 : BN * kBK * 2);
+      const uint32_t tx = ((dbg & 1) ? 0 : a_bytes) + ((dbg & 2) ? 0 : BN * kBK * 2);
       for (int kb = 0; kb < pre; ++kb) {
         if (tx) mbar_expect_tx(&full[kb], tx); else mbar_arrive(&full[kb]);
         if (!(dbg & 2)) tma_load_2d_hint(smem + kb * Cfg::kStageBytes + Cfg::kABytes, &tmB, &full[kb], kb * kBK, n0, kEvictFirst);
@@ -230,7 +230,10 @@ template <int BM, int BN, int EPI>
 static int launch_tc(const void* x, const void* w, int rows, int N, int K, const EpiParams& P, cudaStream_t st) {
   using Cfg = GemmCfg<BM, BN>;
   TensorMap tmA, tmB;
-  int rc = make_tmap_bf16_2d(&tmA, x, (uint64_t)rows, (uint64_t)K, (uint64_t)K * 2, BM, kBK, true);
+  // the activation box is as tall as the tensor when that is less than a tile: TMA would zero-fill the rest at the cost of
+  // real bytes (the MMA then reads stale shared memory for those rows; their accumulator lanes are never read back)
+  const uint32_t a_rows = rows < BM ? (uint32_t)((rows + 7) / 8 * 8) : (uint32_t)BM;
+  int rc = make_tmap_bf16_2d(&tmA, x, (uint64_t)rows, (uint64_t)K, (uint64_t)K * 2, a_rows, kBK, true);
   if (rc) return rc;
   rc = make_tmap_bf16_2d(&tmB, w, (uint64_t)N, (uint64_t)K, (uint64_t)K * 2, BN, kBK, true);
   if (rc) return rc;
@@ -239,7 +242,7 @@ static int launch_tc(const void* x, const void* w, int rows, int N, int K, const
   VLG_CUDA(attr_once([&] { return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes); }));
   dim3 grid(N / BN, (rows + BM - 1) / BM);
   static const int dbg = [] { const char* e = getenv("VLG_GEMM_DEBUG"); return e ? atoi(e) : 0; }();
-  VLG_CUDA(launch_kernel(kern, grid, dim3(kGemmThreads), Cfg::kSmemBytes, st, tmA, tmB, rows, K, P, dbg));
+  VLG_CUDA(launch_kernel(kern, grid, dim3(kGemmThreads), Cfg::kSmemBytes, st, tmA, tmB, rows, K, P, dbg, a_rows * (uint32_t)(kBK * 2)));
   VLG_LAUNCH_CHECK();
   return VLG_OK;
 }

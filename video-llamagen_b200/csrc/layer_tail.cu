@@ -73,6 +73,8 @@ struct LtParams {
   unsigned* bar;             // [0] grid-barrier arrivals, [1] exit arrivals; both zero between launches
   volatile unsigned* err;    // mapped host word: set when a grid barrier gave up waiting (see lt_grid_barrier)
   int dbg;
+  uint32_t a_bytes;          // bytes of one activation tile as TMA delivers it: round8(rows) x 128 (the MMA reads 128 rows; the
+                             // rows beyond are whatever the stage held before -- they only feed accumulator lanes nobody reads)
   int fast_silu;             // SwiGLU epilogue: ex2.approx / rcp.approx instead of expf + IEEE division (A/B: VLG_LT_FASTSILU)
   // L2 prefetch of what the NEXT kernel streams from HBM (see lt_pf_slice): the K/V prefix of the next layer's attention,
   // and/or one flat region (the head GEMM's weights after the last layer)
@@ -231,11 +233,11 @@ __device__ __forceinline__ void lt_pf_slice(const LtParams& P, int slice, int n_
 // g: k-blocks this CTA has pushed through the ring so far (producer and MMA issuer walk the same sequence);
 // acc_uses: GEMM phases in which this CTA owned a unit (parity of acc_ready).
 template <int ST, int SB>
-__device__ __forceinline__ void lt_prefetch_b(const LtGemm& G, const TensorMap* tmB, uint8_t* ring, LtSmem<ST>& sm, uint32_t g) {
+__device__ __forceinline__ void lt_prefetch_b(const LtGemm& G, const TensorMap* tmB, uint8_t* ring, LtSmem<ST>& sm, uint32_t g, uint32_t P_a_bytes) {
   const LtUnit v = lt_unit(G, blockIdx.x);
   if (!v.valid) return;
   const int pre = v.nkb < ST ? v.nkb : ST;
-  const uint32_t tx = kLtABytes + G.BN * 128;
+  const uint32_t tx = P_a_bytes + G.BN * 128;
   for (int kb = 0; kb < pre; ++kb) {
     const uint32_t s = (g + kb) % ST, it = (g + kb) / ST;
     mbar_wait(&sm.empty[s], (it & 1) ^ 1);
@@ -263,7 +265,7 @@ __device__ __forceinline__ void lt_gemm_phase(const LtGemm& G, const TensorMap* 
           const uint32_t s = (g + kb) % ST;
           tma_load_2d_hint(ring + s * SB, tmA, &sm.full[s], (u.kb0 + kb) * 64, 0, kEvictLast);
         }
-        const uint32_t tx = kLtABytes + G.BN * 128;
+        const uint32_t tx = P.a_bytes + G.BN * 128;
         for (int kb = pre; kb < u.nkb; ++kb) {
           const uint32_t s = (g + kb) % ST, it = (g + kb) / ST;
           mbar_wait(&sm.empty[s], (it & 1) ^ 1);
@@ -273,7 +275,7 @@ __device__ __forceinline__ void lt_gemm_phase(const LtGemm& G, const TensorMap* 
           tma_load_2d_hint(a + kLtABytes, tmB, &sm.full[s], (u.kb0 + kb) * 64, u.n0, kEvictFirst);
         }
       }
-      if (Gnext != nullptr) lt_prefetch_b<ST, SB>(*Gnext, tmBnext, ring, sm, g + nkb);
+      if (Gnext != nullptr) lt_prefetch_b<ST, SB>(*Gnext, tmBnext, ring, sm, g + nkb, P.a_bytes);
     }
     __syncwarp();
   } else if (warp == 1) {
@@ -467,8 +469,8 @@ layer_tail_kernel(const __grid_constant__ TensorMap tmAttn, const __grid_constan
   // the first GEMM's weight tiles do not depend on the previous kernel: request them before waiting for it
   if (warp == 0) {
     if (elect_one()) {
-      if (P.has_front) lt_prefetch_b<ST, SB>(P.g_wo, &tmWo, ring, sm, 0);
-      else if (P.has_qkv) lt_prefetch_b<ST, SB>(P.g_qkv, &tmWqkv, ring, sm, 0);
+      if (P.has_front) lt_prefetch_b<ST, SB>(P.g_wo, &tmWo, ring, sm, 0, P.a_bytes);
+      else if (P.has_qkv) lt_prefetch_b<ST, SB>(P.g_qkv, &tmWqkv, ring, sm, 0, P.a_bytes);
     }
     __syncwarp();
   }
@@ -614,6 +616,11 @@ int launch_layer_tail(const LtLaunch& a, cudaStream_t st) {
   P.dbg = dbg;
   static const int fast_silu = [] { const char* e = getenv("VLG_LT_FASTSILU"); return e ? atoi(e) : 1; }();
   P.fast_silu = fast_silu;
+  // Activation tiles are loaded at their real height: a 128-row box over a 16-row tensor makes TMA zero-fill 14 KB of every
+  // 16 KB tile, and the fill occupies the copy engine like real bytes do.  VLG_LT_FULLBOX=1 restores the padded box (A/B).
+  static const bool full_box = [] { const char* e = getenv("VLG_LT_FULLBOX"); return e && e[0] == '1'; }();
+  const uint32_t a_rows = full_box ? 128u : (uint32_t)((a.rows + 7) / 8 * 8);
+  P.a_bytes = a_rows * 128u;
   // L2 prefetch budget per launch (MB of next-layer K + V).  OFF by default: measured on B200 (gpurun_out of round 2,
   // DESIGN.md 4.1) the attention kernel runs at the same speed from L2-resident K/V as from HBM (its shared-memory / issue
   // side bounds it at ~7.9 TB/s), while the fill traffic adds latency to every phase of this kernel: 819 / 846 / 902 / 954 ms
@@ -628,10 +635,10 @@ int launch_layer_tail(const LtLaunch& a, cudaStream_t st) {
 
   TensorMap tmAttn{}, tmXn{}, tmFfn{}, tmWo{}, tmW13{}, tmW2{}, tmWqkv{};
   int rc;
-  if ((rc = make_tmap_bf16_2d(&tmXn, a.xn, (uint64_t)a.rows, (uint64_t)a.dim, (uint64_t)a.dim * 2, 128, 64, true))) return rc;
+  if ((rc = make_tmap_bf16_2d(&tmXn, a.xn, (uint64_t)a.rows, (uint64_t)a.dim, (uint64_t)a.dim * 2, a_rows, 64, true))) return rc;
   if (P.has_front) {
-    if ((rc = make_tmap_bf16_2d(&tmAttn, a.attn, (uint64_t)a.rows, (uint64_t)a.dim, (uint64_t)a.dim * 2, 128, 64, true))) return rc;
-    if ((rc = make_tmap_bf16_2d(&tmFfn, a.ffn, (uint64_t)a.rows, (uint64_t)a.hidden, (uint64_t)a.hidden * 2, 128, 64, true))) return rc;
+    if ((rc = make_tmap_bf16_2d(&tmAttn, a.attn, (uint64_t)a.rows, (uint64_t)a.dim, (uint64_t)a.dim * 2, a_rows, 64, true))) return rc;
+    if ((rc = make_tmap_bf16_2d(&tmFfn, a.ffn, (uint64_t)a.rows, (uint64_t)a.hidden, (uint64_t)a.hidden * 2, a_rows, 64, true))) return rc;
     if ((rc = make_tmap_bf16_2d(&tmWo, a.wo, (uint64_t)a.dim, (uint64_t)a.dim, (uint64_t)a.dim * 2, P.g_wo.BN, 64, true))) return rc;
     if ((rc = make_tmap_bf16_2d(&tmW13, a.w13, (uint64_t)2 * a.hidden, (uint64_t)a.dim, (uint64_t)a.dim * 2, P.g_w13.BN, 64, true))) return rc;
     if ((rc = make_tmap_bf16_2d(&tmW2, a.w2, (uint64_t)a.dim, (uint64_t)a.hidden, (uint64_t)a.hidden * 2, P.g_w2.BN, 64, true))) return rc;

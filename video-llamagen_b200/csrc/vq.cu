@@ -57,7 +57,6 @@ __global__ void vq_prep_kernel(const float* __restrict__ cb, float* __restrict__
 //   scores: 8-term fma chain <= 5e-7 each; eps = 4e-6 * (|z| + |e|max)^2 covers twice their sum.
 constexpr int kVq2Threads = 128;
 constexpr int kVq2Chunk = 1024;    // codes per shared-memory fill: 1024 * (8 dims * 2 copies + 2) * 4 B = 72 KB
-constexpr int kVq2Group = 8;       // codes whose scores stay in registers between index look-ups
 
 __device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
   return (unsigned long long)__float_as_uint(lo) | ((unsigned long long)__float_as_uint(hi) << 32);
@@ -75,47 +74,48 @@ __device__ __forceinline__ float max3f(float a, float b, float c) {
   return r;
 }
 
-// LP latent pairs per thread (2 * LP latents), C = 8 only.
-template <int LP>
+// LP latent pairs per thread (2 * LP latents), G codes whose scores stay in registers between index look-ups; C = 8 only.
+template <int LP, int G>
 __global__ void __launch_bounds__(kVq2Threads)
 vq_score_kernel(const float* __restrict__ z, const float* __restrict__ en, const float* __restrict__ e2,
                 const float* __restrict__ e2max, int64_t* __restrict__ idx_out, float* __restrict__ zq,
                 unsigned* __restrict__ amb_count, int* __restrict__ amb_list, int64_t N, int64_t HW, int n_e, int l2_norm) {
   constexpr int C = 8, L = 2 * LP;
   extern __shared__ __align__(16) float sm[];
-  float* s_e = sm;                          // [chunk][C][2]: every component twice, so one 64-bit load feeds both halves of an FFMA2
-  float* s_h = sm + kVq2Chunk * C * 2;      // [chunk][2]:   -|e_j|^2 / 2, twice
+  float* s_e = sm;                              // [chunk + 1][C][2]: every component twice, so one 64-bit load feeds both halves of an FFMA2
+  float* s_h = sm + (kVq2Chunk + 1) * C * 2;    // [chunk + 1][2]:   -|e_j|^2 / 2, twice
 
   const int64_t base = (int64_t)blockIdx.x * (kVq2Threads * L) + threadIdx.x;
   unsigned long long zp[LP][C];             // latent pair p = latents (base + (2p) * T, base + (2p+1) * T)
-  float zraw[L][C];
   float z2[L];
 #pragma unroll
-  for (int l = 0; l < L; ++l) {
-    const int64_t n = base + (int64_t)l * kVq2Threads;
-    const bool ok = n < N;
-    const int64_t b = ok ? n / HW : 0, hw = ok ? n % HW : 0;
-    float ss = 0.f;
+  for (int p = 0; p < LP; ++p) {
+    float zr[2][C];
 #pragma unroll
-    for (int c = 0; c < C; ++c) {
-      zraw[l][c] = ok ? z[(b * C + c) * HW + hw] : 0.f;
-      ss = __fadd_rn(ss, __fmul_rn(zraw[l][c], zraw[l][c]));
-    }
-    if (l2_norm) {
-      const float nrm = fmaxf(sqrtf(ss), 1e-12f);
-      ss = 0.f;
+    for (int h = 0; h < 2; ++h) {
+      const int64_t n = base + (int64_t)(2 * p + h) * kVq2Threads;
+      const bool ok = n < N;
+      const int64_t b = ok ? n / HW : 0, hw = ok ? n % HW : 0;
+      float ss = 0.f;
 #pragma unroll
       for (int c = 0; c < C; ++c) {
-        zraw[l][c] = __fdiv_rn(zraw[l][c], nrm);
-        ss = __fadd_rn(ss, __fmul_rn(zraw[l][c], zraw[l][c]));
+        zr[h][c] = ok ? z[(b * C + c) * HW + hw] : 0.f;
+        ss = __fadd_rn(ss, __fmul_rn(zr[h][c], zr[h][c]));
       }
+      if (l2_norm) {
+        const float nrm = fmaxf(sqrtf(ss), 1e-12f);
+        ss = 0.f;
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+          zr[h][c] = __fdiv_rn(zr[h][c], nrm);
+          ss = __fadd_rn(ss, __fmul_rn(zr[h][c], zr[h][c]));
+        }
+      }
+      z2[2 * p + h] = ss;
     }
-    z2[l] = ss;
+#pragma unroll
+    for (int c = 0; c < C; ++c) zp[p][c] = pack2(zr[0][c], zr[1][c]);
   }
-#pragma unroll
-  for (int p = 0; p < LP; ++p)
-#pragma unroll
-    for (int c = 0; c < C; ++c) zp[p][c] = pack2(zraw[2 * p][c], zraw[2 * p + 1][c]);
 
   float best[L], second[L];
   int bidx[L];
@@ -129,20 +129,27 @@ vq_score_kernel(const float* __restrict__ z, const float* __restrict__ en, const
       const float v = en[(size_t)c0 * C + i];
       reinterpret_cast<float2*>(s_e)[i] = make_float2(v, v);
     }
-    for (int i = threadIdx.x; i < kVq2Chunk; i += kVq2Threads) {
+    for (int i = threadIdx.x; i < kVq2Chunk + 1; i += kVq2Threads) {
       const float h = i < cn ? -0.5f * e2[c0 + i] : -INFINITY;        // padding codes can never win
       reinterpret_cast<float2*>(s_h)[i] = make_float2(h, h);
     }
-    if (cn < kVq2Chunk)
-      for (int i = cn * C + threadIdx.x; i < kVq2Chunk * C; i += kVq2Threads) reinterpret_cast<float2*>(s_e)[i] = make_float2(0.f, 0.f);
+    for (int i = cn * C + threadIdx.x; i < (kVq2Chunk + 1) * C; i += kVq2Threads) reinterpret_cast<float2*>(s_e)[i] = make_float2(0.f, 0.f);
     __syncthreads();
-    for (int j0 = 0; j0 < kVq2Chunk; j0 += kVq2Group) {
-      unsigned long long sc[LP][kVq2Group];
+    // e-values of code j + 1 are requested while code j is being multiplied (one code = 4 * LP FFMA2 issue slots, longer
+    // than a shared-memory round trip); the chunk is padded by one code so the look-ahead never leaves it
+    const ulonglong2* ep0 = reinterpret_cast<const ulonglong2*>(s_e);
+    ulonglong2 n01 = ep0[0], n23 = ep0[1], n45 = ep0[2], n67 = ep0[3];
+    unsigned long long nh = reinterpret_cast<const unsigned long long*>(s_h)[0];
+#pragma unroll 1
+    for (int j0 = 0; j0 < kVq2Chunk; j0 += G) {
+      unsigned long long sc[LP][G];
 #pragma unroll
-      for (int j = 0; j < kVq2Group; ++j) {
-        const ulonglong2* ep = reinterpret_cast<const ulonglong2*>(s_e + (size_t)(j0 + j) * C * 2);   // warp-wide broadcasts
-        const ulonglong2 e01 = ep[0], e23 = ep[1], e45 = ep[2], e67 = ep[3];
-        const unsigned long long h = reinterpret_cast<const unsigned long long*>(s_h)[j0 + j];
+      for (int j = 0; j < G; ++j) {
+        const ulonglong2 e01 = n01, e23 = n23, e45 = n45, e67 = n67;
+        const unsigned long long h = nh;
+        const ulonglong2* ep = reinterpret_cast<const ulonglong2*>(s_e + (size_t)(j0 + j + 1) * C * 2);   // warp-wide broadcasts
+        n01 = ep[0]; n23 = ep[1]; n45 = ep[2]; n67 = ep[3];
+        nh = reinterpret_cast<const unsigned long long*>(s_h)[j0 + j + 1];
 #pragma unroll
         for (int p = 0; p < LP; ++p) {
           unsigned long long a = ffma2(zp[p][0], e01.x, h);
@@ -157,15 +164,17 @@ vq_score_kernel(const float* __restrict__ z, const float* __restrict__ en, const
       }
 #pragma unroll
       for (int l = 0; l < L; ++l) {
-        float s[kVq2Group];
+        float s[G];
 #pragma unroll
-        for (int j = 0; j < kVq2Group; ++j) s[j] = (l & 1) ? hi32(sc[l >> 1][j]) : lo32(sc[l >> 1][j]);
-        const float m = max3f(max3f(s[0], s[1], s[2]), max3f(s[3], s[4], s[5]), fmaxf(s[6], s[7]));
+        for (int j = 0; j < G; ++j) s[j] = (l & 1) ? hi32(sc[l >> 1][j]) : lo32(sc[l >> 1][j]);
+        float m;
+        if constexpr (G == 8) m = max3f(max3f(s[0], s[1], s[2]), max3f(s[3], s[4], s[5]), fmaxf(s[6], s[7]));
+        else m = fmaxf(max3f(s[0], s[1], s[2]), s[3]);
         if (m > best[l]) {                   // new record (rare: ~ln(n_e) times per latent): find it, demote the old best
           float run = second[l] > best[l] ? second[l] : best[l];
           int arg = -1;
 #pragma unroll
-          for (int j = 0; j < kVq2Group; ++j) {
+          for (int j = 0; j < G; ++j) {
             if (arg < 0 && s[j] == m) arg = j;                 // first index among equals
             else run = fmaxf(run, s[j]);
           }
@@ -197,7 +206,8 @@ vq_score_kernel(const float* __restrict__ z, const float* __restrict__ en, const
 #pragma unroll
       for (int c = 0; c < C; ++c) {
         const float e = en[(size_t)bidx[l] * C + c];
-        zq[(b * C + c) * HW + hw] = __fadd_rn(zraw[l][c], __fsub_rn(e, zraw[l][c]));
+        const float zv = (l & 1) ? hi32(zp[l >> 1][c]) : lo32(zp[l >> 1][c]);
+        zq[(b * C + c) * HW + hw] = __fadd_rn(zv, __fsub_rn(e, zv));
       }
     }
   }
@@ -428,7 +438,7 @@ namespace vlg {
 // C = 8 with the work area of vlg_vq_scratch_floats(): score-domain FFMA2 kernel + exact recheck of the ambiguous latents
 static int launch_vq_fast(const float* z, const float* cb, int64_t* idx, float* zq, float* scratch, int64_t N, int64_t HW,
                           int n_e, int l2_norm, cudaStream_t st) {
-  constexpr int C = 8, LP = 4;
+  constexpr int C = 8;
   float* en = scratch;
   float* e2 = scratch + (size_t)n_e * C;
   float* e2max = e2 + n_e;                                         // 1 float
@@ -437,14 +447,27 @@ static int launch_vq_fast(const float* z, const float* cb, int64_t* idx, float* 
   VLG_CUDA(cudaMemsetAsync(e2max, 0, 2 * sizeof(float), st));
   vq_prep_kernel<C><<<(n_e + 255) / 256, 256, 0, st>>>(cb, en, e2, n_e, l2_norm, e2max);
   VLG_LAUNCH_CHECK();
-  const size_t smem = (size_t)kVq2Chunk * (C * 2 + 2) * sizeof(float);
-  auto kern = vq_score_kernel<LP>;
-  static PerDeviceOnce once;
-  VLG_CUDA(once([&] { return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); }));
-  const int64_t per_block = (int64_t)kVq2Threads * 2 * LP;
-  kern<<<(unsigned)((N + per_block - 1) / per_block), kVq2Threads, smem, st>>>(z, en, e2, e2max, idx, zq, amb_count, amb_list, N,
-                                                                               HW, n_e, l2_norm);
-  VLG_LAUNCH_CHECK();
+  const size_t smem = (size_t)(kVq2Chunk + 1) * (C * 2 + 2) * sizeof(float);
+  // (latent pairs per thread, codes per register group): measured on B200 by tools/vq_bench.py; VLG_VQ_VARIANT for A/B
+  static const int variant = [] { const char* e = getenv("VLG_VQ_VARIANT"); return e ? atoi(e) : 0; }();
+  auto launch = [&](auto kern, int lp) -> int {
+    VLG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t per_block = (int64_t)kVq2Threads * 2 * lp;
+    kern<<<(unsigned)((N + per_block - 1) / per_block), kVq2Threads, smem, st>>>(z, en, e2, e2max, idx, zq, amb_count, amb_list, N,
+                                                                                 HW, n_e, l2_norm);
+    VLG_LAUNCH_CHECK();
+    return VLG_OK;
+  };
+  int rc;
+  switch (variant) {
+    case 1: rc = launch(vq_score_kernel<6, 4>, 6); break;
+    case 2: rc = launch(vq_score_kernel<3, 4>, 3); break;
+    case 3: rc = launch(vq_score_kernel<3, 8>, 3); break;
+    case 4: rc = launch(vq_score_kernel<2, 8>, 2); break;
+    case 5: rc = launch(vq_score_kernel<4, 8>, 4); break;
+    default: rc = launch(vq_score_kernel<4, 4>, 4); break;
+  }
+  if (rc) return rc;
   vq_recheck_kernel<C><<<num_sms() * 2, 256, 0, st>>>(z, en, e2, idx, zq, amb_count, amb_list, HW, n_e, l2_norm);
   VLG_LAUNCH_CHECK();
   return VLG_OK;
