@@ -247,6 +247,8 @@ int vlg_debug_gemm_timestamps(unsigned long long* out16_host);
 int vlg_debug_trunk_without_attention(vlg_ctx* ctx, int pos, void* stream);
 /* instrumentation (VLG_LT_DEBUG=1): globaltimer phase stamps [160 CTAs][32 slots] of the last full layer-tail launch */
 int vlg_debug_lt_timestamps(unsigned long long* out_host);
+/* the same for the pipelined layer-tail kernel (layer_tail2.cu): per (stage, row group) stamps */
+int vlg_debug_lt2_timestamps(unsigned long long* out_host);
 
 #ifdef __cplusplus
 }

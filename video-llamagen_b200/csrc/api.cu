@@ -11,6 +11,7 @@
 
 #include "common.cuh"
 #include "kernels.h"
+#include "lt_common.cuh"
 
 using namespace vlg;
 
@@ -51,7 +52,7 @@ Layout make_layout(const vlg_geometry& g, int max_rows, int max_seq) {
   L.attn_scratch = take(attn_scratch_bytes(max_rows, g.n_head, D, S));
   L.state = take(sizeof(StepState));
   L.norm_flags = take((size_t)(2 * g.n_layer + 1) * sizeof(unsigned));   // fused-RMSNorm arrival counters, one per norm
-  L.lt_bar = take(2 * sizeof(unsigned));                                   // layer-tail grid-barrier counters
+  L.lt_bar = take(kLtCounterBytes);                                        // layer-tail counters (lt_common.cuh)
   L.lt_part = take(g.dtype == VLG_BF16 ? layer_tail_scratch_bytes(max_rows, g.dim, g.hidden_dim) : 0);   // split-K partials
   L.mask = take((size_t)max_rows * g.cls_token_num);
   L.seq = take((size_t)max_rows * S * sizeof(int32_t));
@@ -116,7 +117,7 @@ int ctx_check(vlg_ctx* c) {
   if (c->err_host == nullptr || *reinterpret_cast<volatile unsigned*>(c->err_host) == 0) return VLG_OK;
   cudaDeviceSynchronize();
   *c->err_host = 0;
-  cudaMemset(c->ws + c->L.lt_bar, 0, 2 * sizeof(unsigned));
+  cudaMemset(c->ws + c->L.lt_bar, 0, kLtCounterBytes);
   set_error("a layer-tail launch timed out in its grid barrier: its %d CTAs were not co-resident (another context, stream or "
             "process was occupying SMs of this GPU); outputs since the previous successful call are invalid", num_sms());
   return VLG_ERR_STATE;
@@ -444,7 +445,7 @@ extern "C" int vlg_ctx_create(const vlg_geometry* g, const vlg_weights* w, int m
   // the reference allocates zeroed caches (gpt.py:174-175); do it once so no stale NaN bit patterns exist
   VLG_CUDA(cudaMemset(c->ws + L.k_cache, 0, L.h - L.k_cache));
   VLG_CUDA(cudaMemset(c->state(), 0, sizeof(StepState)));
-  VLG_CUDA(cudaMemset(c->ws + L.lt_bar, 0, 2 * sizeof(unsigned)));
+  VLG_CUDA(cudaMemset(c->ws + L.lt_bar, 0, kLtCounterBytes));
   VLG_CUDA(cudaDeviceSynchronize());
   *out = c;
   return VLG_OK;

@@ -22,10 +22,7 @@
 //     the reference's rounding points (epilogue.cuh / elementwise.cu).
 //
 // Only the tensor-core tile is re-shaped; no arithmetic of the reference is re-associated except the fp32 K-sum order.
-#include <stdlib.h>
-
-#include "common.cuh"
-#include "kernels.h"
+#include "lt_common.cuh"
 
 namespace vlg {
 
@@ -48,14 +45,6 @@ constexpr int kLtStageBytesNarrow = kLtABytes + 8192;     // weight tile of up t
 constexpr int kLtStagesNarrow = 9;
 constexpr int kLtTmemCols = 128;
 constexpr int lt_smem_bytes(int stages, int stage_bytes) { return stages * stage_bytes + 1024 /*align slack*/ + 512 /*barriers*/; }
-
-struct LtGemm {
-  int N, K;        // out features, in features
-  int BN;          // column tile (32, 64 or 128)
-  int S;           // K splits
-  int n_tiles;     // N / BN
-  int kb_per;      // 64-wide k-blocks per split (the last split may own fewer)
-};
 
 struct LtParams {
   int rows, dim, hidden;
@@ -101,41 +90,6 @@ __device__ unsigned long long g_lt_ts[160 * 32];
     }                                                                                                 \
   } while (0)
 #define LT_TS(i) do { if (threadIdx.x == 0) LT_TS_AT(i); } while (0)
-
-struct LtUnit { int valid, n0, split, kb0, nkb; };
-
-__device__ __forceinline__ LtUnit lt_unit(const LtGemm& G, int cta) {
-  LtUnit u;
-  u.valid = cta < G.n_tiles * G.S;
-  const int tile = cta % G.n_tiles;      // neighbouring CTAs share the activation slice and differ in the weight tile
-  u.split = cta / G.n_tiles;
-  u.n0 = tile * G.BN;
-  u.kb0 = u.split * G.kb_per;
-  const int nkb = G.K / 64;
-  u.nkb = min(G.kb_per, nkb - u.kb0);
-  return u;
-}
-
-__device__ __forceinline__ void stg256(float* p, const float* v) {
-  asm volatile("st.global.cg.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]),
-               "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
-}
-// 16 bf16 (32 bytes = one full L2 sector) in one store
-__device__ __forceinline__ void stg256_bf16x16(__nv_bfloat16* p, const float* o) {
-  asm volatile("st.global.cg.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(pack_bf16(o[0], o[1])), "r"(pack_bf16(o[2], o[3])),
-               "r"(pack_bf16(o[4], o[5])), "r"(pack_bf16(o[6], o[7])), "r"(pack_bf16(o[8], o[9])), "r"(pack_bf16(o[10], o[11])),
-               "r"(pack_bf16(o[12], o[13])), "r"(pack_bf16(o[14], o[15])) : "memory");
-}
-// L2-coherent loads: everything a row phase reads was written by other SMs earlier in this same kernel
-__device__ __forceinline__ void ldg256(const float* p, float* v) {
-  asm volatile("ld.global.cg.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]) : "l"(p));
-}
-__device__ __forceinline__ uint4 ldg128_cg(const void* p) {
-  uint4 r;
-  asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
-  return r;
-}
 
 // All CTAs of the grid are co-resident (grid <= SM count, one CTA per SM): arrive with a release add, poll with acquire.
 // Co-residency holds whenever this context has the GPU's SMs to itself; if some other resident work keeps CTAs of this grid
@@ -366,34 +320,6 @@ __device__ __forceinline__ void lt_gemm_phase(const LtGemm& G, const TensorMap* 
 }
 
 // ---------------------------------------------------------------------------------------------------- row phases
-// sum of the S partials of 8 consecutive columns, fixed order
-__device__ __forceinline__ void lt_reduce8(const float* part, int S, size_t split_stride, size_t off, float* acc) {
-  constexpr int kChunk = 8;          // loads in flight per thread before the first dependent add
-  float t[kChunk][8];
-#pragma unroll
-  for (int j = 0; j < kChunk; ++j)
-    if (j < S) ldg256(part + (size_t)j * split_stride + off, t[j]);
-#pragma unroll
-  for (int i = 0; i < 8; ++i) acc[i] = t[0][i];
-#pragma unroll
-  for (int j = 1; j < kChunk; ++j)
-    if (j < S) {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) acc[i] = __fadd_rn(acc[i], t[j][i]);
-    }
-  for (int s0 = kChunk; s0 < S; s0 += kChunk) {
-#pragma unroll
-    for (int j = 0; j < kChunk; ++j)
-      if (s0 + j < S) ldg256(part + (size_t)(s0 + j) * split_stride + off, t[j]);
-#pragma unroll
-    for (int j = 0; j < kChunk; ++j)
-      if (s0 + j < S) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) acc[i] = __fadd_rn(acc[i], t[j][i]);
-      }
-  }
-}
-
 // h <- T(h + T(sum of partials))  (when G != null), then xn <- T(T(h * rsqrt(mean(h^2) + eps)) * w): one row per CTA
 template <int ST>
 __device__ __forceinline__ void lt_norm_phase(const LtGemm* G, const __nv_bfloat16* w, const LtParams& P, LtSmem<ST>& sm) {
@@ -534,7 +460,7 @@ layer_tail_kernel(const __grid_constant__ TensorMap tmAttn, const __grid_constan
 // (partial tile) and the row phase pulls back, with at most one unit per CTA.
 // Split-K units write fp32 partials: the L2 write path sustains only ~4.3 TB/s over the chip (tools/micro/bar_bench.cu), so
 // a stored byte is costed 4x a loaded one.  Units that own all of K (split == false) need room for one tile per CTA.
-static bool lt_pick(int N, int K, int sms, bool split, LtGemm* out) {
+bool lt_pick(int N, int K, int sms, bool split, LtGemm* out, int max_bn) {
   if (K % 64 != 0 || N % 64 != 0) return false;
   const int nkb = K / 64;
   // split count cap: the row phase that reduces the partials keeps 8 loads per thread in flight per L2 round trip
@@ -543,7 +469,7 @@ static bool lt_pick(int N, int K, int sms, bool split, LtGemm* out) {
   bool found = false;
   const int bns[3] = {32, 64, 128};
   for (int bn : bns) {
-    if (N % bn) continue;
+    if (N % bn || bn > max_bn) continue;
     const int tiles = N / bn;
     if (tiles > sms) continue;
     int s0 = split ? sms / tiles : 1;
@@ -578,16 +504,18 @@ size_t layer_tail_scratch_bytes(int max_rows, int dim, int hidden) {
   const int sms = num_sms();
   size_t worst = 0;
   const int shapes[2][2] = {{dim, dim}, {dim, hidden}};   // wo and w2 are the split-K GEMMs
-  for (auto& sh : shapes) {
-    LtGemm t;
-    if (!lt_pick(sh[0], sh[1], sms, true, &t)) continue;
-    const size_t b = (size_t)t.S * rows * t.N * sizeof(float);
-    if (b > worst) worst = b;
-  }
+  for (auto& sh : shapes)
+    for (int max_bn : {64, 128}) {          // layer_tail2.cu caps the column tile at 64 and may end up with another split count
+      LtGemm t;
+      if (!lt_pick(sh[0], sh[1], sms, true, &t, max_bn)) continue;
+      const size_t b = (size_t)t.S * rows * t.N * sizeof(float);
+      if (b > worst) worst = b;
+    }
   return worst + 1024;
 }
 
 int launch_layer_tail(const LtLaunch& a, cudaStream_t st) {
+  if (layer_tail2_supported(a.rows, a.dim, a.hidden)) return launch_layer_tail2(a, st);   // VLG_LT_V=1 keeps this file's kernel
   VLG_REQUIRE(layer_tail_supported(a.rows, a.dim, a.hidden), "layer_tail: unsupported shape rows=%d dim=%d hidden=%d", a.rows, a.dim, a.hidden);
   VLG_REQUIRE(a.wo || a.wqkv, "layer_tail: nothing to do");
   const int sms = num_sms();
