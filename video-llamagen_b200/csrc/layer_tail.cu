@@ -43,7 +43,8 @@ constexpr int kLtABytes = 128 * 64 * 2;    // activation tile: 128 rows x 64 k
 constexpr int kLtStageBytesWide = 2 * kLtABytes;          // weight tile of up to 128 rows x 64 k
 constexpr int kLtStageBytesNarrow = kLtABytes + 8192;     // weight tile of up to 64 rows x 64 k
 constexpr int kLtStagesNarrow = 9;
-constexpr int kLtTmemCols = 128;
+constexpr int kLtTmemCols = 256;          // two accumulators (one per MMA-issuing warp), 128 columns apart
+constexpr int kLtIssuer2 = 2 + kLtReaders;   // second MMA-issuing warp: the first warp behind the TMEM readers
 constexpr int lt_smem_bytes(int stages, int stage_bytes) { return stages * stage_bytes + 1024 /*align slack*/ + 512 /*barriers*/; }
 
 struct LtParams {
@@ -124,6 +125,13 @@ __device__ __forceinline__ void lt_grid_barrier(unsigned* ctr, unsigned& target,
   }
   __syncthreads();
   tc_fence_after();
+}
+
+__device__ __forceinline__ void lt_add_acc16(uint32_t taddr, float* v) {
+  float u[16];
+  tmem_ld16(taddr, u);
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __fadd_rn(v[i], u[i]);
 }
 
 template <int ST> struct LtSmem {
@@ -232,17 +240,22 @@ __device__ __forceinline__ void lt_gemm_phase(const LtGemm& G, const TensorMap* 
       if (Gnext != nullptr) lt_prefetch_b<ST, SB>(*Gnext, tmBnext, ring, sm, g + nkb, P.a_bytes);
     }
     __syncwarp();
-  } else if (warp == 1) {
+  } else if (warp == 1 || warp == kLtIssuer2) {
+    // Two issuing threads, alternating k-blocks, each into its own accumulator (summed by the readers): one thread sustains a
+    // tcgen05.mma per ~130 cycles whatever the tile shape (tools/micro/mma_issue_bench.cu), i.e. 0.26 us per k-block -- more
+    // than the 0.18-0.22 us the SM's L2 port needs to deliver the k-block's operands.
+    const int j = warp == 1 ? 0 : 1;
     if (u.valid && elect_one()) {
       const uint32_t idesc = umma_idesc_bf16(128, G.BN);
-      for (int kb = 0; kb < u.nkb; ++kb) {
+      const uint32_t acc = tmem_acc + 128u * j;
+      for (int kb = j; kb < u.nkb; kb += 2) {
         const uint32_t s = (g + kb) % ST, it = (g + kb) / ST;
         mbar_wait(&sm.full[s], it & 1);
         tc_fence_after();
         const uint32_t a_addr = smem_u32(ring + s * SB);
         const uint64_t adesc = umma_desc_sw128(a_addr), bdesc = umma_desc_sw128(a_addr + kLtABytes);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_bf16(tmem_acc, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+        for (int k = 0; k < 4; ++k) umma_bf16(acc, adesc + 2 * k, bdesc + 2 * k, idesc, (kb >= 2 || k != 0));
         umma_commit(&sm.empty[s]);
       }
       umma_commit(&sm.acc_ready);
@@ -254,6 +267,7 @@ __device__ __forceinline__ void lt_gemm_phase(const LtGemm& G, const TensorMap* 
       // covers whole 32-byte sectors: partial-sector writes cost the L2 several times their size.
       const int quad = warp & 3, half = (warp - 2) >> 2, r = quad * 32 + lane;
       const uint32_t lane_base = tmem_acc + (static_cast<uint32_t>(quad * 32) << 16);
+      const bool two = u.nkb > 1;            // the second issuer's accumulator holds the odd k-blocks
       mbar_wait(&sm.acc_ready, acc_uses & 1);
       tc_fence_after();
       if (threadIdx.x == 64) LT_TS_AT(ts_slot);
@@ -262,6 +276,7 @@ __device__ __forceinline__ void lt_gemm_phase(const LtGemm& G, const TensorMap* 
         for (int c = half * 16; c < G.BN; c += 16 * kLtHalves) {
           float v[16];
           tmem_ld16(lane_base + c, v);
+          if (two) lt_add_acc16(lane_base + 128 + c, v);
           if (r < P.rows) {
             stg256(dst + c, v);
             stg256(dst + c + 8, v + 8);
@@ -272,6 +287,7 @@ __device__ __forceinline__ void lt_gemm_phase(const LtGemm& G, const TensorMap* 
           float v[32];
           tmem_ld16(lane_base + c, v);
           tmem_ld16(lane_base + c + 16, v + 16);
+          if (two) { lt_add_acc16(lane_base + 128 + c, v); lt_add_acc16(lane_base + 128 + c + 16, v + 16); }
           if (r < P.rows) {
             float o[16];
 #pragma unroll
@@ -289,6 +305,7 @@ __device__ __forceinline__ void lt_gemm_phase(const LtGemm& G, const TensorMap* 
         for (int c = half * 16; c < G.BN; c += 16 * kLtHalves) {
           float v[16];
           tmem_ld16(lane_base + c, v);
+          if (two) lt_add_acc16(lane_base + 128 + c, v);
           if (r < P.rows) {
             const int n = u.n0 + c, sec = n / E.dim, cc = n - sec * E.dim, head = cc / E.D, dd = cc - head * E.D;
             float o[16];
@@ -379,7 +396,7 @@ layer_tail_kernel(const __grid_constant__ TensorMap tmAttn, const __grid_constan
     tma_prefetch_desc(&tmXn);
     if (P.has_qkv) tma_prefetch_desc(&tmWqkv);
     for (int s = 0; s < ST; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], 1); }
-    mbar_init(&sm.acc_ready, 1);
+    mbar_init(&sm.acc_ready, 2);
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc<kLtTmemCols>(&sm.tmem_slot);
