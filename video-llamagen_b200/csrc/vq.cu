@@ -66,6 +66,16 @@ __device__ __forceinline__ unsigned long long ffma2(unsigned long long a, unsign
   asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
   return d;
 }
+__device__ __forceinline__ unsigned long long fmul2(unsigned long long a, unsigned long long b) {
+  unsigned long long d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ unsigned long long fadd2(unsigned long long a, unsigned long long b) {
+  unsigned long long d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
 __device__ __forceinline__ float lo32(unsigned long long v) { return __uint_as_float((unsigned)v); }
 __device__ __forceinline__ float hi32(unsigned long long v) { return __uint_as_float((unsigned)(v >> 32)); }
 __device__ __forceinline__ float max3f(float a, float b, float c) {
@@ -75,7 +85,7 @@ __device__ __forceinline__ float max3f(float a, float b, float c) {
 }
 
 // LP latent pairs per thread (2 * LP latents), G codes whose scores stay in registers between index look-ups; C = 8 only.
-template <int LP, int G>
+template <int LP, int G, bool SPLIT = false>
 __global__ void __launch_bounds__(kVq2Threads)
 vq_score_kernel(const float* __restrict__ z, const float* __restrict__ en, const float* __restrict__ e2,
                 const float* __restrict__ e2max, int64_t* __restrict__ idx_out, float* __restrict__ zq,
@@ -118,9 +128,9 @@ vq_score_kernel(const float* __restrict__ z, const float* __restrict__ en, const
   }
 
   float best[L], second[L];
-  int bidx[L];
+  int bgrp[L];                  // first code of the group of G codes that holds the best score so far
 #pragma unroll
-  for (int l = 0; l < L; ++l) { best[l] = -INFINITY; second[l] = -INFINITY; bidx[l] = 0; }
+  for (int l = 0; l < L; ++l) { best[l] = -INFINITY; second[l] = -INFINITY; bgrp[l] = 0; }
 
   for (int c0 = 0; c0 < n_e; c0 += kVq2Chunk) {
     const int cn = min(kVq2Chunk, n_e - c0);
@@ -152,14 +162,22 @@ vq_score_kernel(const float* __restrict__ z, const float* __restrict__ en, const
         nh = reinterpret_cast<const unsigned long long*>(s_h)[j0 + j + 1];
 #pragma unroll
         for (int p = 0; p < LP; ++p) {
-          unsigned long long a = ffma2(zp[p][0], e01.x, h);
-          a = ffma2(zp[p][1], e01.y, a);
-          a = ffma2(zp[p][2], e23.x, a);
-          a = ffma2(zp[p][3], e23.y, a);
-          a = ffma2(zp[p][4], e45.x, a);
-          a = ffma2(zp[p][5], e45.y, a);
-          a = ffma2(zp[p][6], e67.x, a);
-          sc[p][j] = ffma2(zp[p][7], e67.y, a);
+          if constexpr (SPLIT) {     // two 4-deep chains and an add: twice the independent work per code for one more pipe slot in eight
+            unsigned long long a = ffma2(zp[p][0], e01.x, h), b = fmul2(zp[p][4], e45.x);
+            a = ffma2(zp[p][1], e01.y, a); b = ffma2(zp[p][5], e45.y, b);
+            a = ffma2(zp[p][2], e23.x, a); b = ffma2(zp[p][6], e67.x, b);
+            a = ffma2(zp[p][3], e23.y, a); b = ffma2(zp[p][7], e67.y, b);
+            sc[p][j] = fadd2(a, b);
+          } else {
+            unsigned long long a = ffma2(zp[p][0], e01.x, h);
+            a = ffma2(zp[p][1], e01.y, a);
+            a = ffma2(zp[p][2], e23.x, a);
+            a = ffma2(zp[p][3], e23.y, a);
+            a = ffma2(zp[p][4], e45.x, a);
+            a = ffma2(zp[p][5], e45.y, a);
+            a = ffma2(zp[p][6], e67.x, a);
+            sc[p][j] = ffma2(zp[p][7], e67.y, a);
+          }
         }
       }
 #pragma unroll
@@ -170,22 +188,51 @@ vq_score_kernel(const float* __restrict__ z, const float* __restrict__ en, const
         float m;
         if constexpr (G == 8) m = max3f(max3f(s[0], s[1], s[2]), max3f(s[3], s[4], s[5]), fmaxf(s[6], s[7]));
         else m = fmaxf(max3f(s[0], s[1], s[2]), s[3]);
-        if (m > best[l]) {                   // new record (rare: ~ln(n_e) times per latent): find it, demote the old best
-          float run = second[l] > best[l] ? second[l] : best[l];
-          int arg = -1;
-#pragma unroll
-          for (int j = 0; j < G; ++j) {
-            if (arg < 0 && s[j] == m) arg = j;                 // first index among equals
-            else run = fmaxf(run, s[j]);
-          }
-          second[l] = run;
-          best[l] = m;
-          bidx[l] = c0 + j0 + arg;
-        } else {
-          second[l] = fmaxf(second[l], m);
-        }
+        // Branch-free record keeping at GROUP granularity (which code of the group it was is settled once, after the scan):
+        // a new record demotes the old best to runner-up, anything else competes for runner-up; equal maxima keep the earlier
+        // group (first index) and leave a zero gap, which sends the latent to the exact recheck.  Eight independent 5-instruction
+        // chains per iteration instead of eight convergence-barrier regions (ncu: those held the FMA pipe at 55 %).
+        second[l] = fmaxf(second[l], fminf(m, best[l]));
+        bgrp[l] = m > best[l] ? c0 + j0 : bgrp[l];
+        best[l] = fmaxf(best[l], m);
       }
     }
+  }
+
+  // which code of the winning group, and the runner-up inside it: the group's scores again, with the loop's arithmetic
+  // (an FFMA2 lane is an IEEE fma, the scalar chain below reproduces it bit for bit)
+  int bidx[L];
+#pragma unroll
+  for (int l = 0; l < L; ++l) {
+    float zl[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) zl[c] = (l & 1) ? hi32(zp[l >> 1][c]) : lo32(zp[l >> 1][c]);
+    int arg = -1;
+    float run = second[l];
+#pragma unroll
+    for (int j = 0; j < G; ++j) {
+      const int code = bgrp[l] + j;
+      float a = -INFINITY;
+      if (code < n_e) {
+        const float* e = en + (size_t)code * C;
+        a = -0.5f * e2[code];
+        if constexpr (SPLIT) {
+          float b = __fmul_rn(zl[4], e[4]);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) a = __fmaf_rn(zl[c], e[c], a);
+#pragma unroll
+          for (int c = 5; c < 8; ++c) b = __fmaf_rn(zl[c], e[c], b);
+          a = __fadd_rn(a, b);
+        } else {
+#pragma unroll
+          for (int c = 0; c < C; ++c) a = __fmaf_rn(zl[c], e[c], a);
+        }
+      }
+      if (arg < 0 && a == best[l]) arg = j;                  // first index among equals
+      else run = fmaxf(run, a);
+    }
+    second[l] = arg < 0 ? best[l] : run;                     // no match (NaN scores): zero gap, the recheck decides
+    bidx[l] = bgrp[l] + (arg < 0 ? 0 : arg);
   }
 
   const float emax = e2max ? *e2max : 1.f;
@@ -465,6 +512,9 @@ static int launch_vq_fast(const float* z, const float* cb, int64_t* idx, float* 
     case 3: rc = launch(vq_score_kernel<3, 8>, 3); break;
     case 4: rc = launch(vq_score_kernel<2, 8>, 2); break;
     case 5: rc = launch(vq_score_kernel<4, 8>, 4); break;
+    case 6: rc = launch(vq_score_kernel<4, 4, true>, 4); break;
+    case 7: rc = launch(vq_score_kernel<4, 8, true>, 4); break;
+    case 8: rc = launch(vq_score_kernel<3, 8, true>, 3); break;
     default: rc = launch(vq_score_kernel<4, 4>, 4); break;
   }
   if (rc) return rc;
