@@ -299,6 +299,57 @@ def extra_cfg5(dev):
             "algorithmic_flops": 2 * n * 16384 * 8}}
 
 
+def _conv_flops(module, x_shape):
+    """2 * MACs of every Conv2d of `module` for one forward at input x_shape, counted with forward hooks on meta tensors."""
+    import torch
+    total = [0]
+
+    def hook(m, inp, out):
+        total[0] += 2 * out.numel() * m.in_channels * m.kernel_size[0] * m.kernel_size[1] // m.groups
+    hs = [m.register_forward_hook(hook) for m in module.modules() if isinstance(m, torch.nn.Conv2d)]
+    try:
+        with torch.no_grad():
+            module(torch.zeros(x_shape, device="meta"))
+    finally:
+        for h in hs:
+            h.remove()
+    return total[0]
+
+
+def extra_decode_code(dev, pk, n_images=64, grid=24):
+    """The call right after generate() in every sampler (sample_t2i.py:134): code indices -> images through
+    VQModel.decode_code.  The codebook gather + post_quant_conv is one vlg kernel; the decoder CNN is library convolutions
+    (cuDNN through torch, TF32 allowed as the reference scripts set it, sample_t2i.py:2-4) -- tensor-bound, so the fraction is
+    against the measured dense bf16 GEMM peak halved (TF32 runs at half the bf16 rate)."""
+    import copy
+    import torch
+    from vlg.vq_model import VQ_models
+    torch.manual_seed(0)
+    vq = VQ_models["VQ-16"](codebook_size=16384, codebook_embed_dim=8).eval()
+    flops = _conv_flops(copy.deepcopy(vq.decoder).to("meta"), (1, 256, grid, grid))
+    vq = vq.to(dev)
+    codes = torch.randint(0, 16384, (n_images * grid * grid,), device=dev)
+    shape = (n_images, 8, grid, grid)
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        with torch.no_grad():
+            for _ in range(2):
+                img = vq.decode_code(codes, shape)
+            ms, _ = _timed_ms(lambda: vq.decode_code(codes, shape), 5)
+            ms_front, _ = _timed_ms(lambda: vq.quantize.decode_front(codes, shape, vq.post_quant_conv.weight, vq.post_quant_conv.bias), 20)
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+    tf = flops * n_images / ms / 1e9
+    peak = pk.get("bf16_tflops", 1603.9) / 2
+    return {"workload": f"decode_code: {n_images} x {grid}x{grid} codes -> {n_images} x 3 x {grid * 16}x{grid * 16} images (VQ-16 decoder, fp32 / TF32 convolutions)",
+            "value": round(n_images / ms * 1e3, 1), "unit": "images/s", "ms": round(ms, 2), "image_shape": list(img.shape),
+            "fused_gather_post_quant_conv_ms": round(ms_front, 4),
+            "roofline": {"bound": "tensor", "achieved": round(tf, 1), "peak": round(peak, 1), "unit": "TFLOP/s", "frac": round(tf / peak, 4),
+                         "peak_source": "MEASURED_PEAKS.json bf16_tflops / 2 (TF32)", "conv_flops_per_image": flops,
+                         "note": "library convolutions (cuDNN): outside the hand-written hot path, reported because it is the wall-clock tail after generate()"}}
+
+
 def extra_gpu_eager(dev, decode_steps):
     """The reference algorithm (oracle port: torch library kernels, the reference's op sequence incl. its full-cache
     attention) in bf16 on this GPU, on the sample the CPU leg runs: the like-for-like successor of the A100 eager column of
@@ -536,6 +587,7 @@ def run_vlg(args):
             for name, fn in (("python_driven_loop", lambda: extra_python_loop(model, cond_dev)),
                              ("gpu_eager_baseline", lambda: extra_gpu_eager(dev, args.ref_decode_steps)),
                              ("cfg5_vq", lambda: extra_cfg5(dev)),
+                             ("decode_code", lambda: extra_decode_code(dev, pk)),
                              ("cfg3", lambda: extra_cfg3(dev, peak_scale)),
                              ("cfg4_b8", lambda: extra_cfg4(dev, peak_scale, 8))):
                 try:

@@ -10,10 +10,10 @@ from vlg.gpt import GPT_models
 from vlg.generate import generate
 lib = L.lib()
 torch.manual_seed(0)
-m = GPT_models["GPT-L"](block_size=576, cls_token_num=1, model_type="c2i").eval()
+m = GPT_models[os.environ.get("VLG_PH_MODEL", "GPT-L")](block_size=576, cls_token_num=1, model_type="c2i").eval()
 torch.nn.init.normal_(m.output.weight, std=0.02)
 m = m.to("cuda", torch.bfloat16)
-cond = torch.randint(0, 1000, (64,)).cuda()
+cond = torch.randint(0, 1000, (int(os.environ.get("VLG_PH_BATCH", "64")),)).cuda()
 n_new = int(sys.argv[1]) if len(sys.argv) > 1 else 288
 names = {0: "start", 1: "pdl_wait", 2: "wo issued", 3: "bar", 4: "norm1", 5: "bar", 6: "w13 issued", 7: "bar", 8: "w2 issued",
          9: "bar", 10: "norm2", 11: "bar", 12: "qkv issued", 16: "wo acc", 17: "wo epi", 18: "w13 acc", 19: "w13 epi",

@@ -511,11 +511,11 @@ static int launch_vq_fast(const float* z, const float* cb, int64_t* idx, float* 
     case 2: rc = launch(vq_score_kernel<3, 4>, 3); break;
     case 3: rc = launch(vq_score_kernel<3, 8>, 3); break;
     case 4: rc = launch(vq_score_kernel<2, 8>, 2); break;
-    case 5: rc = launch(vq_score_kernel<4, 8>, 4); break;
+    case 5: rc = launch(vq_score_kernel<4, 4>, 4); break;
     case 6: rc = launch(vq_score_kernel<4, 4, true>, 4); break;
     case 7: rc = launch(vq_score_kernel<4, 8, true>, 4); break;
     case 8: rc = launch(vq_score_kernel<3, 8, true>, 3); break;
-    default: rc = launch(vq_score_kernel<4, 4>, 4); break;
+    default: rc = launch(vq_score_kernel<4, 8>, 4); break;   // 6.64 ms / 1M latents (4, 4: 6.91; split chains: 7.0-7.4)
   }
   if (rc) return rc;
   vq_recheck_kernel<C><<<num_sms() * 2, 256, 0, st>>>(z, en, e2, idx, zq, amb_count, amb_list, HW, n_e, l2_norm);
