@@ -393,3 +393,43 @@ def test_generate_loop_tokens_follow_the_distribution():
     for frac, cnt in ((float((t[:, 1:] == t[:, :-1]).float().mean()), B * (N - 1)),       # consecutive steps
                       (float((t[1:] == t[:-1]).float().mean()), (B - 1) * N)):            # neighbouring rows
         assert abs(frac - same) < 6 * (same * (1 - same) / cnt) ** 0.5, (frac, same)
+
+
+def test_two_contexts_on_two_streams_do_not_share_the_layer_tail_kernel():
+    """the layer-tail kernel's grid barriers need every CTA resident, which two contexts decoding at the same time
+    on one GPU cannot both have.  The second context must notice that the first one's work is still in flight and run the
+    per-op kernels for that call (more launches, no grid barrier), and go back to the layer-tail kernel once the device is
+    its own again -- no hang, no error word, tokens valid."""
+    from vlg import _lib as L
+    lib = L.lib()
+    torch.manual_seed(0)
+    models = []
+    for _ in range(2):
+        m = GPT_models["GPT-B"](block_size=256, cls_token_num=1, model_type="c2i").eval()
+        torch.nn.init.normal_(m.output.weight, std=0.02)
+        models.append(m.to(DEV, torch.bfloat16))
+    cond = torch.randint(0, 1000, (8,), device=DEV)
+    kw = dict(cfg_scale=4.0, temperature=1.0, top_k=100, top_p=1.0, sample_logits=True)
+    N = 128
+    for m in models:                                    # warm-up: contexts, graphs
+        generate(m, cond, N, seed=1, **kw)
+    torch.cuda.synchronize()
+    sa, sb = torch.cuda.Stream(), torch.cuda.Stream()
+    n0 = lib.vlg_launch_count()
+    with torch.cuda.stream(sa):
+        ta = generate(models[0], cond, N, seed=2, **kw)
+    n1 = lib.vlg_launch_count()
+    with torch.cuda.stream(sb):
+        tb = generate(models[1], cond, N, seed=2, **kw)  # enqueued while the first generate is still running
+    n2 = lib.vlg_launch_count()
+    torch.cuda.synchronize()
+    with torch.cuda.stream(sb):
+        tb2 = generate(models[1], cond, N, seed=2, **kw)  # alone again
+    n3 = lib.vlg_launch_count()
+    torch.cuda.synchronize()
+    for t in (ta, tb, tb2):
+        assert t.shape == (8, N) and int(t.min()) >= 0 and int(t.max()) < 16384
+    for m in models:
+        m._engine.check()                               # raises if a grid barrier timed out
+    assert n3 - n2 == n1 - n0, "an undisturbed context uses the layer-tail kernel"
+    assert n2 - n1 > n1 - n0, "the concurrent context must have fallen back to the per-op kernels"

@@ -6,6 +6,7 @@
 // decode step is a fixed kernel sequence: it is captured once into a CUDA graph and replayed N-1 times
 // with no host synchronisation and no per-step host work besides cudaGraphLaunch.
 #include <stdlib.h>
+#include <mutex>
 #include <vector>
 #include <cuda_profiler_api.h>
 
@@ -88,6 +89,7 @@ struct vlg_ctx {
   bool force_generic_attn = false;   // VLG_ATTN=generic: A/B the two attention kernels
   bool skip_attention = false;       // measurement only (vlg_debug_trunk_without_attention)
   bool no_fused_norm = true;         // VLG_FUSED_NORM=1 enables the fused RMSNorm prologue of the GEMMs (A/B)
+  bool lt_ok = true;                 // this call may use the layer-tail kernel (lt_claim below); false -> per-op kernels
   // graph capture is illegal on the legacy default stream (torch's default): such callers are forked onto this one
   cudaStream_t own_stream = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
@@ -98,10 +100,10 @@ struct vlg_ctx {
   // cached decode-step graph
   cudaGraphExec_t graph = nullptr;
   cudaGraphExec_t graph_v = nullptr;   // t2v decode step (vlg_generate_t2v)
-  struct KeyV { int rows, B, N, cfg_interval, has_mask; float cfg_scale; void* out; } key_v{};
+  struct KeyV { int rows, B, N, cfg_interval, has_mask, lt; float cfg_scale; void* out; } key_v{};
   uint64_t step_kernels_v = 0;
   uint64_t step_kernels = 0;   // kernels per replayed decode step
-  struct Key { int rows, B, N, top_k, sample_logits, cfg_interval, has_mask; float cfg_scale, temperature, top_p; } key{};
+  struct Key { int rows, B, N, top_k, sample_logits, cfg_interval, has_mask, lt; float cfg_scale, temperature, top_p; } key{};
 
   template <typename T> T* at(size_t off) const { return reinterpret_cast<T*>(ws + off); }
   void* kc(int layer) const { return ws + L.k_cache + (size_t)layer * max_rows * g.n_head * S_max * D * esz(g.dtype); }
@@ -121,6 +123,37 @@ int ctx_check(vlg_ctx* c) {
   set_error("a layer-tail launch timed out in its grid barrier: its %d CTAs were not co-resident (another context, stream or "
             "process was occupying SMs of this GPU); outputs since the previous successful call are invalid", num_sms());
   return VLG_ERR_STATE;
+}
+
+
+// The layer-tail kernel's grid barriers need all of its CTAs resident at once, which holds while nothing else of this process
+// keeps SMs of the device busy with a layer-tail launch of its own.  Every API call that may launch it claims the device:
+// the claim succeeds when the last layer-tail work enqueued on this device belongs to this context or has completed
+// (event query, no synchronisation); otherwise this call runs the per-op kernels (VLG_LT=0 path: slower, no grid barrier).
+// lt_release records the event behind the enqueued work.  Other PROCESSES on the same GPU cannot be seen from here: for
+// them the barrier's bounded wait and the error word (ctx_check) remain the backstop.
+struct LtDeviceClaim { vlg_ctx* owner = nullptr; cudaEvent_t ev = nullptr; };
+LtDeviceClaim g_lt_claim[kMaxDevices];
+std::mutex g_lt_mu;
+
+bool lt_claim(vlg_ctx* c) {
+  std::lock_guard<std::mutex> lk(g_lt_mu);
+  LtDeviceClaim& d = g_lt_claim[current_device()];
+  c->lt_ok = d.owner == nullptr || d.owner == c || d.ev == nullptr || cudaEventQuery(d.ev) == cudaSuccess;
+  if (!c->lt_ok) cudaGetLastError();                       // cudaErrorNotReady is not an error
+  return c->lt_ok;
+}
+void lt_release(vlg_ctx* c, cudaStream_t st) {
+  if (!c->lt_ok) return;
+  std::lock_guard<std::mutex> lk(g_lt_mu);
+  LtDeviceClaim& d = g_lt_claim[current_device()];
+  if (d.ev == nullptr && cudaEventCreateWithFlags(&d.ev, cudaEventDisableTiming) != cudaSuccess) { d.ev = nullptr; return; }
+  if (cudaEventRecord(d.ev, st) == cudaSuccess) d.owner = c;
+}
+void lt_forget(vlg_ctx* c) {
+  std::lock_guard<std::mutex> lk(g_lt_mu);
+  for (LtDeviceClaim& d : g_lt_claim)
+    if (d.owner == c) d.owner = nullptr;
 }
 
 __global__ void set_state_kernel(StepState* s, int step, int pos, unsigned long long seed) {
@@ -195,7 +228,7 @@ int run_trunk(vlg_ctx* c, const int* pos_ptr, int pos_imm, int max_pos, bool fus
   void* attn = c->at<void>(c->L.attn);
   void* ffn = c->at<void>(c->L.ffn);
   unsigned* flags = c->at<unsigned>(c->L.norm_flags);
-  if (g.dtype == VLG_BF16 && layer_tail_supported(R, d, hid)) {
+  if (g.dtype == VLG_BF16 && c->lt_ok && layer_tail_supported(R, d, hid)) {
     // Persistent layer-tail kernel: [norm + wqkv] in front of layer 0, then per layer attention + one launch that runs
     // wo .. w2 of that layer and the norm + wqkv of the next one (the final norm after the last layer).
     auto rope_params = [&](int l) {
@@ -350,7 +383,7 @@ int run_head(vlg_ctx* c, float* logits, bool fused_final_norm, cudaStream_t st) 
   EpiParams P{};
   P.out = logits;
   P.ld_out = c->g.vocab_size;
-  if (fused_final_norm && c->g.dtype == VLG_BF16 && !c->no_fused_norm && !layer_tail_supported(c->rows, c->g.dim, c->g.hidden_dim)) {
+  if (fused_final_norm && c->g.dtype == VLG_BF16 && !c->no_fused_norm && !(c->lt_ok && layer_tail_supported(c->rows, c->g.dim, c->g.hidden_dim))) {
     P.norm_src = c->at<void>(c->L.h); P.norm_weight = c->w.norm; P.norm_dst = c->at<void>(c->L.xn);
     P.norm_flag = c->at<unsigned>(c->L.norm_flags) + 2 * c->g.n_layer; P.norm_eps = c->g.norm_eps;
   }
@@ -453,6 +486,7 @@ extern "C" int vlg_ctx_create(const vlg_geometry* g, const vlg_weights* w, int m
 
 extern "C" void vlg_ctx_destroy(vlg_ctx* c) {
   if (!c) return;
+  lt_forget(c);
   if (c->graph) cudaGraphExecDestroy(c->graph);
   if (c->graph_v) cudaGraphExecDestroy(c->graph_v);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
@@ -501,7 +535,10 @@ extern "C" int vlg_forward_pos(vlg_ctx* c, const int64_t* tokens_dev, const int6
   }
   if (rc) return rc;
   const bool fuse_final = logits_dev != nullptr && hidden_dev == nullptr;   // the normed hidden is materialised only on request
-  if ((rc = run_trunk(c, nullptr, pos, pos, fuse_final, st))) return rc;
+  lt_claim(c);
+  rc = run_trunk(c, nullptr, pos, pos, fuse_final, st);
+  lt_release(c, st);
+  if (rc) return rc;
   if (hidden_dev)
     VLG_CUDA(cudaMemcpyAsync(hidden_dev, c->at<void>(c->L.xn), (size_t)c->rows * g.dim * esz(g.dtype),
                              cudaMemcpyDeviceToDevice, st));
@@ -551,10 +588,16 @@ extern "C" int vlg_generate(vlg_ctx* c, const vlg_generate_params* pp, const voi
   if (int rc0 = ctx_check(c)) return rc0;
   cudaStream_t user = (cudaStream_t)stream;
   const bool legacy = user == nullptr || user == cudaStreamLegacy || user == cudaStreamPerThread;
-  if (!legacy) return generate_on(c, pp, cond_dev, uncond_dev, emb_masks_dev, tokens_dev, user);
+  lt_claim(c);
+  if (!legacy) {
+    const int rc = generate_on(c, pp, cond_dev, uncond_dev, emb_masks_dev, tokens_dev, user);
+    lt_release(c, user);
+    return rc;
+  }
   VLG_CUDA(cudaEventRecord(c->ev_fork, user));
   VLG_CUDA(cudaStreamWaitEvent(c->own_stream, c->ev_fork, 0));
   int rc = generate_on(c, pp, cond_dev, uncond_dev, emb_masks_dev, tokens_dev, c->own_stream);
+  lt_release(c, c->own_stream);
   VLG_CUDA(cudaEventRecord(c->ev_join, c->own_stream));
   VLG_CUDA(cudaStreamWaitEvent(user, c->ev_join, 0));
   return rc;
@@ -621,7 +664,7 @@ static int generate_on(vlg_ctx* c, const vlg_generate_params* pp, const void* co
 
   // ---- decode loop (generate.py:105-124) as a replayed CUDA graph
   if (N > 1) {
-    vlg_ctx::Key k{rows, p.B, N, p.top_k, p.sample_logits, p.cfg_interval, c->has_mask ? 1 : 0, p.cfg_scale, p.temperature, p.top_p};
+    vlg_ctx::Key k{rows, p.B, N, p.top_k, p.sample_logits, p.cfg_interval, c->has_mask ? 1 : 0, c->lt_ok ? 1 : 0, p.cfg_scale, p.temperature, p.top_p};
     if (!c->graph || memcmp(&k, &c->key, sizeof(k)) != 0) {
       if (c->graph) { cudaGraphExecDestroy(c->graph); c->graph = nullptr; }
       cudaGraph_t graph = nullptr;
@@ -743,7 +786,7 @@ int generate_t2v_on(vlg_ctx* c, const vlg_generate_params* pp, const void* cond_
 
   // ---- decode loop as a replayed CUDA graph
   if (N > 1) {
-    vlg_ctx::KeyV k{rows, p.B, N, p.cfg_interval, c->has_mask ? 1 : 0, p.cfg_scale, latents_dev};
+    vlg_ctx::KeyV k{rows, p.B, N, p.cfg_interval, c->has_mask ? 1 : 0, c->lt_ok ? 1 : 0, p.cfg_scale, latents_dev};
     if (!c->graph_v || memcmp(&k, &c->key_v, sizeof(k)) != 0) {
       if (c->graph_v) { cudaGraphExecDestroy(c->graph_v); c->graph_v = nullptr; }
       cudaGraph_t graph = nullptr;
@@ -777,10 +820,16 @@ extern "C" int vlg_generate_t2v(vlg_ctx* c, const vlg_generate_params* pp, const
   if (int rc0 = ctx_check(c)) return rc0;
   cudaStream_t user = (cudaStream_t)stream;
   const bool legacy = user == nullptr || user == cudaStreamLegacy || user == cudaStreamPerThread;
-  if (!legacy) return generate_t2v_on(c, pp, cond_dev, uncond_dev, emb_masks_dev, latents_dev, user);
+  lt_claim(c);
+  if (!legacy) {
+    const int rc = generate_t2v_on(c, pp, cond_dev, uncond_dev, emb_masks_dev, latents_dev, user);
+    lt_release(c, user);
+    return rc;
+  }
   VLG_CUDA(cudaEventRecord(c->ev_fork, user));
   VLG_CUDA(cudaStreamWaitEvent(c->own_stream, c->ev_fork, 0));
   int rc = generate_t2v_on(c, pp, cond_dev, uncond_dev, emb_masks_dev, latents_dev, c->own_stream);
+  lt_release(c, c->own_stream);
   VLG_CUDA(cudaEventRecord(c->ev_join, c->own_stream));
   VLG_CUDA(cudaStreamWaitEvent(user, c->ev_join, 0));
   return rc;
@@ -833,6 +882,7 @@ extern "C" int vlg_debug_trunk_without_attention(vlg_ctx* c, int pos, void* stre
               "vlg_debug_trunk_without_attention: the layer-tail kernel does not run for this shape");
   VLG_REQUIRE(pos >= 0 && pos < c->S_max && pos < c->w.rope_rows, "vlg_debug_trunk_without_attention: pos %d out of range", pos);
   c->skip_attention = true;
+  c->lt_ok = true;
   const int rc = run_trunk(c, nullptr, pos, pos, false, (cudaStream_t)stream);
   c->skip_attention = false;
   return rc;
