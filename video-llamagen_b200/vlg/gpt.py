@@ -396,6 +396,9 @@ class Transformer(nn.Module):
 
 
 # ------------------------------------------------------------------------------- configs (gpt.py:441-470)
+# All eight names construct (same parameters, same state_dict keys as the reference).  The decode kernels are written for
+# head_dim = 64 -- GPT-B / L / XL / XXL / XXXL / 1B: every BASELINE config; GPT-3B (head_dim 100) and GPT-7B (128) build and
+# load checkpoints but `vlg_ctx_create` refuses them with VLG_ERR_ARG at the first setup_caches() / forward.
 def GPT_7B(**kwargs):
     return Transformer(ModelArgs(n_layer=32, n_head=32, dim=4096, **kwargs))
 
