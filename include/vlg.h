@@ -54,8 +54,9 @@ const char* vlg_last_error(void);
  * codebook_dev fp32 [n_e, C]    raw embedding.weight (normalised inside when l2_norm != 0)
  * idx_dev      int64 [B*HW]     argmin_j ( |z|^2 + |e_j|^2 - 2 z.e_j ), first index on ties
  * zq_dev       fp32 [B, C, HW]  selected (normalised) codebook rows, channel-first; may be NULL
- * scratch_dev  fp32 [vlg_vq_scratch_floats(B*HW, C, n_e)] work area: normalised codebook, |e_j|^2 and the list of
- *              latents whose two best codes are closer than fp32 rounding (settled by an exact second pass) */
+ * scratch_dev  fp32 [vlg_vq_scratch_floats(B*HW, C, n_e)] work area, 16-byte aligned: normalised codebook, |e_j|^2, the
+ *              duplicated / padded codebook layout the score kernel streams, and the list of latents whose two best codes
+ *              are closer than fp32 rounding (settled by an exact second pass) */
 size_t vlg_vq_scratch_floats(int64_t N, int C, int n_e);
 int vlg_vq_argmin(const float* z_dev, const float* codebook_dev, int64_t* idx_dev, float* zq_dev,
                   float* scratch_dev, int64_t B, int C, int64_t HW, int n_e, int l2_norm, void* stream);

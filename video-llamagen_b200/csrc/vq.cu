@@ -16,11 +16,20 @@
 namespace vlg {
 
 // normalise the codebook rows and precompute |e_j|^2 (F.normalize eps = 1e-12, vq_model.py:224); *e2max = max_j |e_j|^2
+// en2 / h2 (optional): the layout vq_score_kernel streams with bulk copies -- every component twice ([j][C][2]) and
+// -|e_j|^2 / 2 twice ([j][2]), padded to n_pad entries with codes that can never win (zeros, -inf)
 template <int C>
 __global__ void vq_prep_kernel(const float* __restrict__ cb, float* __restrict__ en, float* __restrict__ e2, int n_e,
-                               int l2_norm, float* __restrict__ e2max) {
+                               int l2_norm, float* __restrict__ e2max, float* __restrict__ en2, float* __restrict__ h2, int n_pad) {
   int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= n_e) return;
+  if (j >= n_e) {
+    if (en2 != nullptr && j < n_pad) {
+#pragma unroll
+      for (int c = 0; c < C; ++c) reinterpret_cast<float2*>(en2)[(size_t)j * C + c] = make_float2(0.f, 0.f);
+      reinterpret_cast<float2*>(h2)[j] = make_float2(-INFINITY, -INFINITY);
+    }
+    return;
+  }
   float e[C];
 #pragma unroll
   for (int c = 0; c < C; ++c) e[c] = cb[(size_t)j * C + c];
@@ -40,6 +49,12 @@ __global__ void vq_prep_kernel(const float* __restrict__ cb, float* __restrict__
   }
   e2[j] = s2;
   if (e2max) atomicMax(reinterpret_cast<int*>(e2max), __float_as_int(s2));   // s2 >= 0: int order == float order
+  if (en2 != nullptr) {
+#pragma unroll
+    for (int c = 0; c < C; ++c) reinterpret_cast<float2*>(en2)[(size_t)j * C + c] = make_float2(e[c], e[c]);
+    const float h = -0.5f * s2;
+    reinterpret_cast<float2*>(h2)[j] = make_float2(h, h);
+  }
 }
 
 
@@ -56,7 +71,13 @@ __global__ void vq_prep_kernel(const float* __restrict__ cb, float* __restrict__
 //   noise budget (unit-norm rows, |z| = |e| = 1): reference d_j: ulp(2)/2 + ulp(d)/2 + 2 * 8-term dot error <= 1.3e-6,
 //   scores: 8-term fma chain <= 5e-7 each; eps = 4e-6 * (|z| + |e|max)^2 covers twice their sum.
 constexpr int kVq2Threads = 128;
-constexpr int kVq2Chunk = 1024;    // codes per shared-memory fill: 1024 * (8 dims * 2 copies + 2) * 4 B = 72 KB
+constexpr int kVq2Chunk = 512;     // codes per shared-memory buffer; two buffers, the next chunk lands (one bulk copy of the
+                                   // pre-duplicated codebook, issued by one thread) while this one is multiplied: a block no
+                                   // longer stops for ~10 % of its time to fill 72 KB with 128 threads
+constexpr int kVq2Pad = 2;         // entries copied past a chunk: the one-code look-ahead reads the next chunk's first code
+constexpr int kVq2BufE = (kVq2Chunk + kVq2Pad) * 8 * 2;   // floats per buffer, e part
+constexpr int kVq2BufH = (kVq2Chunk + kVq2Pad) * 2;       // floats per buffer, h part
+constexpr int vq2_padded(int n_e) { return (n_e + kVq2Chunk - 1) / kVq2Chunk * kVq2Chunk + kVq2Pad; }
 
 __device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
   return (unsigned long long)__float_as_uint(lo) | ((unsigned long long)__float_as_uint(hi) << 32);
@@ -76,6 +97,11 @@ __device__ __forceinline__ unsigned long long fadd2(unsigned long long a, unsign
   asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
   return d;
 }
+// 1D bulk copy global -> shared (bytes a multiple of 16), completes on an mbarrier
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ float lo32(unsigned long long v) { return __uint_as_float((unsigned)v); }
 __device__ __forceinline__ float hi32(unsigned long long v) { return __uint_as_float((unsigned)(v >> 32)); }
 __device__ __forceinline__ float max3f(float a, float b, float c) {
@@ -86,14 +112,32 @@ __device__ __forceinline__ float max3f(float a, float b, float c) {
 
 // LP latent pairs per thread (2 * LP latents), G codes whose scores stay in registers between index look-ups; C = 8 only.
 template <int LP, int G, bool SPLIT = false>
-__global__ void __launch_bounds__(kVq2Threads)
+__global__ void __launch_bounds__(kVq2Threads, LP <= 4 ? 3 : 1)
 vq_score_kernel(const float* __restrict__ z, const float* __restrict__ en, const float* __restrict__ e2,
-                const float* __restrict__ e2max, int64_t* __restrict__ idx_out, float* __restrict__ zq,
+                const float* __restrict__ e2max, const float* __restrict__ en2, const float* __restrict__ h2,
+                int64_t* __restrict__ idx_out, float* __restrict__ zq,
                 unsigned* __restrict__ amb_count, int* __restrict__ amb_list, int64_t N, int64_t HW, int n_e, int l2_norm) {
   constexpr int C = 8, L = 2 * LP;
-  extern __shared__ __align__(16) float sm[];
-  float* s_e = sm;                              // [chunk + 1][C][2]: every component twice, so one 64-bit load feeds both halves of an FFMA2
-  float* s_h = sm + (kVq2Chunk + 1) * C * 2;    // [chunk + 1][2]:   -|e_j|^2 / 2, twice
+  extern __shared__ __align__(128) float sm[];
+  // two buffers of [chunk + pad][C][2] (every component twice, so one 64-bit load feeds both halves of an FFMA2) and
+  // [chunk + pad][2] (-|e_j|^2 / 2, twice), then the two "landed" mbarriers
+  float* s_e_buf = sm;
+  float* s_h_buf = sm + 2 * kVq2BufE;
+  uint64_t* s_full = reinterpret_cast<uint64_t*>(sm + 2 * kVq2BufE + 2 * kVq2BufH);
+  const int n_chunks = (n_e + kVq2Chunk - 1) / kVq2Chunk;
+  auto fetch = [&](int chunk) {                 // one thread: both parts of a chunk, one mbarrier
+    const int b = chunk & 1;
+    mbar_expect_tx(&s_full[b], (kVq2BufE + kVq2BufH) * 4);
+    bulk_g2s(s_e_buf + b * kVq2BufE, en2 + (size_t)chunk * kVq2Chunk * C * 2, kVq2BufE * 4, &s_full[b]);
+    bulk_g2s(s_h_buf + b * kVq2BufH, h2 + (size_t)chunk * kVq2Chunk * 2, kVq2BufH * 4, &s_full[b]);
+  };
+  if (threadIdx.x == 0) {
+    mbar_init(&s_full[0], 1);
+    mbar_init(&s_full[1], 1);
+    fence_mbar_init();
+    fetch(0);
+  }
+  __syncthreads();
 
   const int64_t base = (int64_t)blockIdx.x * (kVq2Threads * L) + threadIdx.x;
   unsigned long long zp[LP][C];             // latent pair p = latents (base + (2p) * T, base + (2p+1) * T)
@@ -132,21 +176,15 @@ vq_score_kernel(const float* __restrict__ z, const float* __restrict__ en, const
 #pragma unroll
   for (int l = 0; l < L; ++l) { best[l] = -INFINITY; second[l] = -INFINITY; bgrp[l] = 0; }
 
-  for (int c0 = 0; c0 < n_e; c0 += kVq2Chunk) {
-    const int cn = min(kVq2Chunk, n_e - c0);
-    __syncthreads();
-    for (int i = threadIdx.x; i < cn * C; i += kVq2Threads) {
-      const float v = en[(size_t)c0 * C + i];
-      reinterpret_cast<float2*>(s_e)[i] = make_float2(v, v);
-    }
-    for (int i = threadIdx.x; i < kVq2Chunk + 1; i += kVq2Threads) {
-      const float h = i < cn ? -0.5f * e2[c0 + i] : -INFINITY;        // padding codes can never win
-      reinterpret_cast<float2*>(s_h)[i] = make_float2(h, h);
-    }
-    for (int i = cn * C + threadIdx.x; i < (kVq2Chunk + 1) * C; i += kVq2Threads) reinterpret_cast<float2*>(s_e)[i] = make_float2(0.f, 0.f);
-    __syncthreads();
+  for (int chunk = 0; chunk < n_chunks; ++chunk) {
+    const int c0 = chunk * kVq2Chunk;
+    // the other buffer was last read a chunk ago (everyone passed the barrier that closed it): refill it while this one is used
+    if (threadIdx.x == 0 && chunk + 1 < n_chunks) fetch(chunk + 1);
+    while (!mbar_try_wait(&s_full[chunk & 1], (chunk >> 1) & 1)) {}
+    const float* s_e = s_e_buf + (chunk & 1) * kVq2BufE;
+    const float* s_h = s_h_buf + (chunk & 1) * kVq2BufH;
     // e-values of code j + 1 are requested while code j is being multiplied (one code = 4 * LP FFMA2 issue slots, longer
-    // than a shared-memory round trip); the chunk is padded by one code so the look-ahead never leaves it
+    // than a shared-memory round trip); a buffer holds kVq2Pad codes past its chunk so the look-ahead never leaves it
     const ulonglong2* ep0 = reinterpret_cast<const ulonglong2*>(s_e);
     ulonglong2 n01 = ep0[0], n23 = ep0[1], n45 = ep0[2], n67 = ep0[3];
     unsigned long long nh = reinterpret_cast<const unsigned long long*>(s_h)[0];
@@ -197,6 +235,7 @@ vq_score_kernel(const float* __restrict__ z, const float* __restrict__ en, const
         best[l] = fmaxf(best[l], m);
       }
     }
+    __syncthreads();                            // this buffer may be refilled from now on
   }
 
   // which code of the winning group, and the runner-up inside it: the group's scores again, with the loop's arithmetic
@@ -467,7 +506,7 @@ static int launch_vq(const float* z, const float* cb, int64_t* idx, float* zq, f
                      int n_e, int l2_norm, cudaStream_t st) {
   float* en = scratch;
   float* e2 = scratch + (size_t)n_e * C;
-  vq_prep_kernel<C><<<(n_e + 255) / 256, 256, 0, st>>>(cb, en, e2, n_e, l2_norm, nullptr);
+  vq_prep_kernel<C><<<(n_e + 255) / 256, 256, 0, st>>>(cb, en, e2, n_e, l2_norm, nullptr, nullptr, nullptr, 0);
   VLG_LAUNCH_CHECK();
   size_t smem = (size_t)kVqChunk * (C + 1) * sizeof(float);
   auto kern = vq_argmin_kernel<C, L>;
@@ -490,18 +529,22 @@ static int launch_vq_fast(const float* z, const float* cb, int64_t* idx, float* 
   float* e2 = scratch + (size_t)n_e * C;
   float* e2max = e2 + n_e;                                         // 1 float
   unsigned* amb_count = reinterpret_cast<unsigned*>(e2max + 1);    // 1 word
-  int* amb_list = reinterpret_cast<int*>(e2max + 2);               // N words
+  const int n_pad = vq2_padded(n_e);
+  float* en2 = e2max + 4;                                          // [n_pad][C][2], 16-byte aligned (the scratch base is)
+  float* h2 = en2 + (size_t)n_pad * C * 2;                         // [n_pad][2]
+  int* amb_list = reinterpret_cast<int*>(h2 + (size_t)n_pad * 2);  // N words
+  VLG_REQUIRE((reinterpret_cast<uintptr_t>(en2) & 15) == 0, "vlg_vq_argmin: scratch must be 16-byte aligned");
   VLG_CUDA(cudaMemsetAsync(e2max, 0, 2 * sizeof(float), st));
-  vq_prep_kernel<C><<<(n_e + 255) / 256, 256, 0, st>>>(cb, en, e2, n_e, l2_norm, e2max);
+  vq_prep_kernel<C><<<(n_pad + 255) / 256, 256, 0, st>>>(cb, en, e2, n_e, l2_norm, e2max, en2, h2, n_pad);
   VLG_LAUNCH_CHECK();
-  const size_t smem = (size_t)(kVq2Chunk + 1) * (C * 2 + 2) * sizeof(float);
+  const size_t smem = (size_t)(2 * kVq2BufE + 2 * kVq2BufH) * sizeof(float) + 2 * sizeof(uint64_t);
   // (latent pairs per thread, codes per register group): measured on B200 by tools/vq_bench.py; VLG_VQ_VARIANT for A/B
   static const int variant = [] { const char* e = getenv("VLG_VQ_VARIANT"); return e ? atoi(e) : 0; }();
   auto launch = [&](auto kern, int lp) -> int {
     VLG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t per_block = (int64_t)kVq2Threads * 2 * lp;
-    kern<<<(unsigned)((N + per_block - 1) / per_block), kVq2Threads, smem, st>>>(z, en, e2, e2max, idx, zq, amb_count, amb_list, N,
-                                                                                 HW, n_e, l2_norm);
+    kern<<<(unsigned)((N + per_block - 1) / per_block), kVq2Threads, smem, st>>>(z, en, e2, e2max, en2, h2, idx, zq, amb_count, amb_list,
+                                                                                 N, HW, n_e, l2_norm);
     VLG_LAUNCH_CHECK();
     return VLG_OK;
   };
@@ -511,11 +554,11 @@ static int launch_vq_fast(const float* z, const float* cb, int64_t* idx, float* 
     case 2: rc = launch(vq_score_kernel<3, 4>, 3); break;
     case 3: rc = launch(vq_score_kernel<3, 8>, 3); break;
     case 4: rc = launch(vq_score_kernel<2, 8>, 2); break;
-    case 5: rc = launch(vq_score_kernel<4, 4>, 4); break;
+    case 5: rc = launch(vq_score_kernel<4, 8>, 4); break;
     case 6: rc = launch(vq_score_kernel<4, 4, true>, 4); break;
     case 7: rc = launch(vq_score_kernel<4, 8, true>, 4); break;
     case 8: rc = launch(vq_score_kernel<3, 8, true>, 3); break;
-    default: rc = launch(vq_score_kernel<4, 8>, 4); break;   // 6.64 ms / 1M latents (4, 4: 6.91; split chains: 7.0-7.4)
+    default: rc = launch(vq_score_kernel<4, 4>, 4); break;   // 6.52 ms / 1M latents ((4, 8): 6.55, spills at the 168-register cap; split chains: 6.8)
   }
   if (rc) return rc;
   vq_recheck_kernel<C><<<num_sms() * 2, 256, 0, st>>>(z, en, e2, idx, zq, amb_count, amb_list, HW, n_e, l2_norm);
@@ -525,7 +568,9 @@ static int launch_vq_fast(const float* z, const float* cb, int64_t* idx, float* 
 }  // namespace vlg
 
 extern "C" size_t vlg_vq_scratch_floats(int64_t N, int C, int n_e) {
-  return (size_t)n_e * (C + 1) + 2 + (size_t)(N > 0 ? N : 0);
+  // normalised codebook, |e|^2, {max |e|^2, ambiguous count, 2 spare}, the duplicated padded layout of the score kernel, list
+  const size_t n_pad = (size_t)vlg::vq2_padded(n_e);
+  return (size_t)n_e * (C + 1) + 4 + n_pad * ((size_t)C * 2 + 2) + (size_t)(N > 0 ? N : 0);
 }
 
 extern "C" int vlg_vq_argmin(const float* z_dev, const float* codebook_dev, int64_t* idx_dev, float* zq_dev,
