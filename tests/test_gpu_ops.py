@@ -362,3 +362,19 @@ def test_loop_branch_equals_api_branch_for_the_same_seed_and_step():
         agree += int((a == b).sum())
         n += B
     assert agree >= n - 3, (agree, n)      # __logf is good to ~1e-6 relative: a flip needs a ~1e-6 near-tie of the top 2
+
+
+@pytest.mark.parametrize("rows,N,K,bnp", [(128, 256, 256, 128), (128, 1024, 1024, 128), (128, 384, 512, 64), (96, 256, 192, 128), (16, 128, 64, 64)])
+def test_pair_gemm_cta_group_2(rows, N, K, bnp):
+    """The CTA-pair building block (tcgen05.mma.cta_group::2, 2-SM TMA loads on the leader's barrier, multicast commits, the
+    2x2 accumulator layout) against a plain fp32 matmul of the same bf16 operands."""
+    from vlg import _lib as L
+    g = torch.Generator().manual_seed(rows * 7 + N)
+    x = torch.randn(rows, K, generator=g).to(DEV, torch.bfloat16)
+    w = (torch.randn(N, K, generator=g) * 0.1).to(DEV, torch.bfloat16)
+    out = torch.full((rows, N), float("nan"), device=DEV, dtype=torch.float32)
+    L.check(L.lib().vlg_debug_pair_gemm(L.ptr(x), L.ptr(w), L.ptr(out), rows, N, K, bnp, L.stream()))
+    torch.cuda.synchronize()
+    ref = x.float() @ w.float().t()
+    assert torch.isfinite(out).all()
+    assert torch.allclose(out, ref, rtol=1e-4, atol=1e-3), f"max err {(out - ref).abs().max().item()}"
