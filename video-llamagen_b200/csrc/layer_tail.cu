@@ -43,6 +43,10 @@ constexpr int kLtABytes = 128 * 64 * 2;    // activation tile: 128 rows x 64 k
 constexpr int kLtStageBytesWide = 2 * kLtABytes;          // weight tile of up to 128 rows x 64 k
 constexpr int kLtStageBytesNarrow = kLtABytes + 8192;     // weight tile of up to 64 rows x 64 k
 constexpr int kLtStagesNarrow = 9;
+// pair mode (see lt_gemm_phase): a stage = this CTA's 64 activation rows + its half (<= 64 rows) of the pair's weight tile
+constexpr int kLtPairABytes = 64 * 128;
+constexpr int kLtStageBytesPair = kLtPairABytes + 8192;
+constexpr int kLtStagesPair = 13;
 constexpr int kLtTmemCols = 256;          // two accumulators (one per MMA-issuing warp), 128 columns apart
 constexpr int kLtIssuer2 = 2 + kLtReaders;   // second MMA-issuing warp: the first warp behind the TMEM readers
 constexpr int lt_smem_bytes(int stages, int stage_bytes) { return stages * stage_bytes + 1024 /*align slack*/ + 512 /*barriers*/; }
@@ -194,50 +198,83 @@ __device__ __forceinline__ void lt_pf_slice(const LtParams& P, int slice, int n_
 // ---------------------------------------------------------------------------------------------------- GEMM phase
 // g: k-blocks this CTA has pushed through the ring so far (producer and MMA issuer walk the same sequence);
 // acc_uses: GEMM phases in which this CTA owned a unit (parity of acc_ready).
-template <int ST, int SB>
+// Unit of this CTA in a GEMM phase.  PAIR: the two CTAs of a cluster own one unit; rank r loads activation rows [64 r, 64 r + 64)
+// and rows [n0 + r BN/2, + BN/2) of the weight tile, the leader (rank 0) issues ONE tcgen05.mma.cta_group::2 per K step that
+// reads both halves (pair_gemm.cu is the verified reference of the mechanics): the bytes through each SM's L2 port drop from
+// (128 + BN) to (64 + BN/2) rows per k-block.  `full` barriers live in the leader and count the bytes of both CTAs.
+template <bool PAIR> __device__ __forceinline__ int lt_unit_id() { return PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x; }
+
+template <int ST, int SB, bool PAIR>
 __device__ __forceinline__ void lt_prefetch_b(const LtGemm& G, const TensorMap* tmB, uint8_t* ring, LtSmem<ST>& sm, uint32_t g, uint32_t P_a_bytes) {
-  const LtUnit v = lt_unit(G, blockIdx.x);
+  const LtUnit v = lt_unit(G, lt_unit_id<PAIR>());
   if (!v.valid) return;
   const int pre = v.nkb < ST ? v.nkb : ST;
-  const uint32_t tx = P_a_bytes + G.BN * 128;
-  for (int kb = 0; kb < pre; ++kb) {
-    const uint32_t s = (g + kb) % ST, it = (g + kb) / ST;
-    mbar_wait(&sm.empty[s], (it & 1) ^ 1);
-    mbar_expect_tx(&sm.full[s], tx);
-    tma_load_2d_hint(ring + s * SB + kLtABytes, tmB, &sm.full[s], (v.kb0 + kb) * 64, v.n0, kEvictFirst);
+  if constexpr (PAIR) {
+    const uint32_t rank = blockIdx.x & 1, tx = 2 * (kLtPairABytes + G.BN * 64);
+    for (int kb = 0; kb < pre; ++kb) {
+      const uint32_t s = (g + kb) % ST, it = (g + kb) / ST;
+      mbar_wait(&sm.empty[s], (it & 1) ^ 1);
+      if (rank == 0) mbar_expect_tx(&sm.full[s], tx);
+      tma_load_2d_pair(ring + s * SB + kLtPairABytes, tmB, &sm.full[s], (v.kb0 + kb) * 64, v.n0 + (int)rank * (G.BN >> 1), kEvictFirst);
+    }
+  } else {
+    const uint32_t tx = P_a_bytes + G.BN * 128;
+    for (int kb = 0; kb < pre; ++kb) {
+      const uint32_t s = (g + kb) % ST, it = (g + kb) / ST;
+      mbar_wait(&sm.empty[s], (it & 1) ^ 1);
+      mbar_expect_tx(&sm.full[s], tx);
+      tma_load_2d_hint(ring + s * SB + kLtABytes, tmB, &sm.full[s], (v.kb0 + kb) * 64, v.n0, kEvictFirst);
+    }
   }
 }
 
 // MODE: -1 = store the fp32 partial tile (split-K, reduced by the following row phase); EPI_SWIGLU / EPI_QKV_ROPE = the unit
 // owns all of K and applies the elementwise tail straight from TMEM (lane == row).
-template <int MODE, int ST, int SB>
+template <int MODE, int ST, int SB, bool PAIR>
 __device__ __forceinline__ void lt_gemm_phase(const LtGemm& G, const TensorMap* tmA, const TensorMap* tmB,
                                               const LtGemm* Gnext, const TensorMap* tmBnext, const LtParams& P,
                                               const EpiParams& E, uint8_t* ring, LtSmem<ST>& sm, uint32_t tmem_acc, uint32_t& g, uint32_t& acc_uses,
                                               int ts_slot) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const LtUnit u = lt_unit(G, blockIdx.x);
+  const LtUnit u = lt_unit(G, lt_unit_id<PAIR>());
   const uint32_t nkb = u.valid ? (uint32_t)u.nkb : 0u;
+  const uint32_t rank = PAIR ? (blockIdx.x & 1) : 0u;
   if (warp == 0) {
     if (elect_one()) {
       asm volatile("fence.proxy.async;" ::: "memory");     // other SMs' generic-proxy stores of A -> this SM's TMA reads
       if (u.valid) {
         const int pre = u.nkb < ST ? u.nkb : ST;      // their weight tiles + expect_tx were issued a phase ago
-        for (int kb = 0; kb < pre; ++kb) {
-          const uint32_t s = (g + kb) % ST;
-          tma_load_2d_hint(ring + s * SB, tmA, &sm.full[s], (u.kb0 + kb) * 64, 0, kEvictLast);
-        }
-        const uint32_t tx = P.a_bytes + G.BN * 128;
-        for (int kb = pre; kb < u.nkb; ++kb) {
-          const uint32_t s = (g + kb) % ST, it = (g + kb) / ST;
-          mbar_wait(&sm.empty[s], (it & 1) ^ 1);
-          mbar_expect_tx(&sm.full[s], tx);
-          uint8_t* a = ring + s * SB;
-          tma_load_2d_hint(a, tmA, &sm.full[s], (u.kb0 + kb) * 64, 0, kEvictLast);
-          tma_load_2d_hint(a + kLtABytes, tmB, &sm.full[s], (u.kb0 + kb) * 64, u.n0, kEvictFirst);
+        if constexpr (PAIR) {
+          for (int kb = 0; kb < pre; ++kb) {
+            const uint32_t s = (g + kb) % ST;
+            tma_load_2d_pair(ring + s * SB, tmA, &sm.full[s], (u.kb0 + kb) * 64, (int)rank * 64, kEvictLast);
+          }
+          const uint32_t tx = 2 * (kLtPairABytes + G.BN * 64);
+          for (int kb = pre; kb < u.nkb; ++kb) {
+            const uint32_t s = (g + kb) % ST, it = (g + kb) / ST;
+            mbar_wait(&sm.empty[s], (it & 1) ^ 1);
+            if (rank == 0) mbar_expect_tx(&sm.full[s], tx);
+            uint8_t* a = ring + s * SB;
+            tma_load_2d_pair(a, tmA, &sm.full[s], (u.kb0 + kb) * 64, (int)rank * 64, kEvictLast);
+            tma_load_2d_pair(a + kLtPairABytes, tmB, &sm.full[s], (u.kb0 + kb) * 64, u.n0 + (int)rank * (G.BN >> 1), kEvictFirst);
+          }
+        } else {
+          for (int kb = 0; kb < pre; ++kb) {
+            const uint32_t s = (g + kb) % ST;
+            tma_load_2d_hint(ring + s * SB, tmA, &sm.full[s], (u.kb0 + kb) * 64, 0, kEvictLast);
+          }
+          const uint32_t tx = P.a_bytes + G.BN * 128;
+          for (int kb = pre; kb < u.nkb; ++kb) {
+            const uint32_t s = (g + kb) % ST, it = (g + kb) / ST;
+            mbar_wait(&sm.empty[s], (it & 1) ^ 1);
+            mbar_expect_tx(&sm.full[s], tx);
+            uint8_t* a = ring + s * SB;
+            tma_load_2d_hint(a, tmA, &sm.full[s], (u.kb0 + kb) * 64, 0, kEvictLast);
+            tma_load_2d_hint(a + kLtABytes, tmB, &sm.full[s], (u.kb0 + kb) * 64, u.n0, kEvictFirst);
+          }
         }
       }
-      if (Gnext != nullptr) lt_prefetch_b<ST, SB>(*Gnext, tmBnext, ring, sm, g + nkb, P.a_bytes);
+      if (Gnext != nullptr) lt_prefetch_b<ST, SB, PAIR>(*Gnext, tmBnext, ring, sm, g + nkb, P.a_bytes);
     }
     __syncwarp();
   } else if (warp == 1 || warp == kLtIssuer2) {
@@ -245,49 +282,62 @@ __device__ __forceinline__ void lt_gemm_phase(const LtGemm& G, const TensorMap* 
     // tcgen05.mma per ~130 cycles whatever the tile shape (tools/micro/mma_issue_bench.cu), i.e. 0.26 us per k-block -- more
     // than the 0.18-0.22 us the SM's L2 port needs to deliver the k-block's operands.
     const int j = warp == 1 ? 0 : 1;
-    if (u.valid && elect_one()) {
+    if (u.valid && rank == 0 && elect_one()) {
       const uint32_t idesc = umma_idesc_bf16(128, G.BN);
-      const uint32_t acc = tmem_acc + 128u * j;
+      const uint32_t acc = tmem_acc + (PAIR ? 64u : 128u) * j;    // a pair's accumulator is BN/2 <= 64 columns wide
       for (int kb = j; kb < u.nkb; kb += 2) {
         const uint32_t s = (g + kb) % ST, it = (g + kb) / ST;
         mbar_wait(&sm.full[s], it & 1);
         tc_fence_after();
         const uint32_t a_addr = smem_u32(ring + s * SB);
-        const uint64_t adesc = umma_desc_sw128(a_addr), bdesc = umma_desc_sw128(a_addr + kLtABytes);
+        const uint64_t adesc = umma_desc_sw128(a_addr), bdesc = umma_desc_sw128(a_addr + (PAIR ? kLtPairABytes : kLtABytes));
+        if constexpr (PAIR) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_bf16(acc, adesc + 2 * k, bdesc + 2 * k, idesc, (kb >= 2 || k != 0));
-        umma_commit(&sm.empty[s]);
+          for (int k = 0; k < 4; ++k) umma_bf16_pair(acc, adesc + 2 * k, bdesc + 2 * k, idesc, (kb >= 2 || k != 0));
+          umma_commit_pair(&sm.empty[s]);
+        } else {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_bf16(acc, adesc + 2 * k, bdesc + 2 * k, idesc, (kb >= 2 || k != 0));
+          umma_commit(&sm.empty[s]);
+        }
       }
-      umma_commit(&sm.acc_ready);
+      if constexpr (PAIR) umma_commit_pair(&sm.acc_ready);
+      else umma_commit(&sm.acc_ready);
     }
     __syncwarp();
   } else if (warp < 2 + kLtReaders) {
     if (u.valid) {
       // TMEM lane quadrant = warp % 4 (hardware rule); the two warps of a quadrant split the columns.  Every store below
       // covers whole 32-byte sectors: partial-sector writes cost the L2 several times their size.
-      const int quad = warp & 3, half = (warp - 2) >> 2, r = quad * 32 + lane;
+      // PAIR: this CTA holds rows [64 rank, 64 rank + 64) in the 2x2 layout -- lanes [0, 64) carry columns [0, BN/2) of the
+      // pair's tile, lanes [64, 128) columns [BN/2, BN) -- so a quadrant's two warps split BN/2 columns, not BN.
+      const int quad = warp & 3, half = (warp - 2) >> 2;
+      const int r = PAIR ? (int)rank * 64 + (quad & 1) * 32 + lane : quad * 32 + lane;
+      const int ncol = PAIR ? (G.BN >> 1) : G.BN;                 // columns on this warp's lanes
+      const int cbase = PAIR ? (quad >> 1) * (G.BN >> 1) : 0;     // tile column of TMEM column 0 on these lanes
+      constexpr uint32_t kAcc2 = PAIR ? 64u : 128u;               // TMEM column distance of the second issuer's accumulator
       const uint32_t lane_base = tmem_acc + (static_cast<uint32_t>(quad * 32) << 16);
       const bool two = u.nkb > 1;            // the second issuer's accumulator holds the odd k-blocks
       mbar_wait(&sm.acc_ready, acc_uses & 1);
       tc_fence_after();
       if (threadIdx.x == 64) LT_TS_AT(ts_slot);
       if constexpr (MODE < 0) {
-        float* dst = P.part + ((size_t)u.split * P.rows + r) * G.N + u.n0;
-        for (int c = half * 16; c < G.BN; c += 16 * kLtHalves) {
+        float* dst = P.part + ((size_t)u.split * P.rows + r) * G.N + u.n0 + cbase;
+        for (int c = half * 16; c < ncol; c += 16 * kLtHalves) {
           float v[16];
           tmem_ld16(lane_base + c, v);
-          if (two) lt_add_acc16(lane_base + 128 + c, v);
+          if (two) lt_add_acc16(lane_base + kAcc2 + c, v);
           if (r < P.rows) {
             stg256(dst + c, v);
             stg256(dst + c + 8, v + 8);
           }
         }
       } else if constexpr (MODE == EPI_SWIGLU) {      // gpt.py:167 -- w1/w3 rows interleaved: columns (2j, 2j+1) = (w1 x, w3 x)_j
-        for (int c = half * 32; c < G.BN; c += 32 * kLtHalves) {
+        for (int c = half * 32; c < ncol; c += 32 * kLtHalves) {
           float v[32];
           tmem_ld16(lane_base + c, v);
           tmem_ld16(lane_base + c + 16, v + 16);
-          if (two) { lt_add_acc16(lane_base + 128 + c, v); lt_add_acc16(lane_base + 128 + c + 16, v + 16); }
+          if (two) { lt_add_acc16(lane_base + kAcc2 + c, v); lt_add_acc16(lane_base + kAcc2 + c + 16, v + 16); }
           if (r < P.rows) {
             float o[16];
 #pragma unroll
@@ -297,17 +347,17 @@ __device__ __forceinline__ void lt_gemm_phase(const LtGemm& G, const TensorMap* 
               const float sl = P.fast_silu ? __fdividef(a, 1.0f + __expf(-a)) : silu_f(a);
               o[i] = __fmul_rn(rnd<__nv_bfloat16>(sl), b);
             }
-            stg256_bf16x16(static_cast<__nv_bfloat16*>(E.out) + (size_t)r * E.ld_out + ((u.n0 + c) >> 1), o);
+            stg256_bf16x16(static_cast<__nv_bfloat16*>(E.out) + (size_t)r * E.ld_out + ((u.n0 + cbase + c) >> 1), o);
           }
         }
       } else {                                         // EPI_QKV_ROPE on 16 columns (a quarter head): gpt.py:215-227, 423-433, 177-185
         const int pos = E.pos_ptr ? *E.pos_ptr : E.pos_imm;
-        for (int c = half * 16; c < G.BN; c += 16 * kLtHalves) {
+        for (int c = half * 16; c < ncol; c += 16 * kLtHalves) {
           float v[16];
           tmem_ld16(lane_base + c, v);
-          if (two) lt_add_acc16(lane_base + 128 + c, v);
+          if (two) lt_add_acc16(lane_base + kAcc2 + c, v);
           if (r < P.rows) {
-            const int n = u.n0 + c, sec = n / E.dim, cc = n - sec * E.dim, head = cc / E.D, dd = cc - head * E.D;
+            const int n = u.n0 + cbase + c, sec = n / E.dim, cc = n - sec * E.dim, head = cc / E.D, dd = cc - head * E.D;
             float o[16];
             if (sec < 2) {
               const float2* tab = reinterpret_cast<const float2*>(E.rope) + (size_t)pos * (E.D >> 1) + (dd >> 1);
@@ -380,7 +430,7 @@ __device__ __forceinline__ void lt_norm_phase(const LtGemm* G, const __nv_bfloat
 }
 
 // ---------------------------------------------------------------------------------------------------- the kernel
-template <int ST, int SB>
+template <int ST, int SB, bool PAIR>
 __global__ void __launch_bounds__(kLtThreads, 1)
 layer_tail_kernel(const __grid_constant__ TensorMap tmAttn, const __grid_constant__ TensorMap tmXn,
                   const __grid_constant__ TensorMap tmFfn, const __grid_constant__ TensorMap tmWo,
@@ -399,9 +449,13 @@ layer_tail_kernel(const __grid_constant__ TensorMap tmAttn, const __grid_constan
     mbar_init(&sm.acc_ready, 2);
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc<kLtTmemCols>(&sm.tmem_slot);
+  if (warp == 1) {
+    if constexpr (PAIR) tmem_alloc_pair<128>(&sm.tmem_slot);     // two accumulators of <= 64 columns
+    else tmem_alloc<kLtTmemCols>(&sm.tmem_slot);
+  }
   tc_fence_before();
   __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();                         // the partner's barriers exist before anything signals them
   tc_fence_after();
   const uint32_t tmem_acc = sm.tmem_slot;
 
@@ -412,8 +466,8 @@ layer_tail_kernel(const __grid_constant__ TensorMap tmAttn, const __grid_constan
   // the first GEMM's weight tiles do not depend on the previous kernel: request them before waiting for it
   if (warp == 0) {
     if (elect_one()) {
-      if (P.has_front) lt_prefetch_b<ST, SB>(P.g_wo, &tmWo, ring, sm, 0, P.a_bytes);
-      else if (P.has_qkv) lt_prefetch_b<ST, SB>(P.g_qkv, &tmWqkv, ring, sm, 0, P.a_bytes);
+      if (P.has_front) lt_prefetch_b<ST, SB, PAIR>(P.g_wo, &tmWo, ring, sm, 0, P.a_bytes);
+      else if (P.has_qkv) lt_prefetch_b<ST, SB, PAIR>(P.g_qkv, &tmWqkv, ring, sm, 0, P.a_bytes);
     }
     __syncwarp();
   }
@@ -424,7 +478,7 @@ layer_tail_kernel(const __grid_constant__ TensorMap tmAttn, const __grid_constan
   int pf_i = 0;
   if (P.has_front) {
     lt_pf_slice(P, pf_i++, pf_slices);
-    lt_gemm_phase<-1, ST, SB>(P.g_wo, &tmAttn, &tmWo, &P.g_w13, &tmW13, P, P.ffn, ring, sm, tmem_acc, g, acc_uses, 16);
+    lt_gemm_phase<-1, ST, SB, PAIR>(P.g_wo, &tmAttn, &tmWo, &P.g_w13, &tmW13, P, P.ffn, ring, sm, tmem_acc, g, acc_uses, 16);
     LT_TS(2);
     lt_grid_barrier(P.bar, bar_target, P.err);
     LT_TS(3);
@@ -434,12 +488,12 @@ layer_tail_kernel(const __grid_constant__ TensorMap tmAttn, const __grid_constan
     lt_grid_barrier(P.bar, bar_target, P.err);
     LT_TS(5);
     lt_pf_slice(P, pf_i++, pf_slices);
-    lt_gemm_phase<EPI_SWIGLU, ST, SB>(P.g_w13, &tmXn, &tmW13, &P.g_w2, &tmW2, P, P.ffn, ring, sm, tmem_acc, g, acc_uses, 18);
+    lt_gemm_phase<EPI_SWIGLU, ST, SB, PAIR>(P.g_w13, &tmXn, &tmW13, &P.g_w2, &tmW2, P, P.ffn, ring, sm, tmem_acc, g, acc_uses, 18);
     LT_TS(6);
     lt_grid_barrier(P.bar, bar_target, P.err);
     LT_TS(7);
     lt_pf_slice(P, pf_i++, pf_slices);
-    lt_gemm_phase<-1, ST, SB>(P.g_w2, &tmFfn, &tmW2, P.has_qkv ? &P.g_qkv : nullptr, &tmWqkv, P, P.ffn, ring, sm, tmem_acc, g, acc_uses, 20);
+    lt_gemm_phase<-1, ST, SB, PAIR>(P.g_w2, &tmFfn, &tmW2, P.has_qkv ? &P.g_qkv : nullptr, &tmWqkv, P, P.ffn, ring, sm, tmem_acc, g, acc_uses, 20);
     LT_TS(8);
     lt_grid_barrier(P.bar, bar_target, P.err);
     LT_TS(9);
@@ -454,7 +508,7 @@ layer_tail_kernel(const __grid_constant__ TensorMap tmAttn, const __grid_constan
     lt_grid_barrier(P.bar, bar_target, P.err);
     LT_TS(11);
     lt_pf_slice(P, pf_i++, pf_slices);
-    lt_gemm_phase<EPI_QKV_ROPE, ST, SB>(P.g_qkv, &tmXn, &tmWqkv, nullptr, nullptr, P, P.rope, ring, sm, tmem_acc, g, acc_uses, 22);
+    lt_gemm_phase<EPI_QKV_ROPE, ST, SB, PAIR>(P.g_qkv, &tmXn, &tmWqkv, nullptr, nullptr, P, P.rope, ring, sm, tmem_acc, g, acc_uses, 22);
     LT_TS(12);
   }
 
@@ -469,7 +523,12 @@ layer_tail_kernel(const __grid_constant__ TensorMap tmAttn, const __grid_constan
       __threadfence();
     }
   }
-  if (warp == 1) tmem_dealloc<kLtTmemCols>(tmem_acc);
+  if constexpr (PAIR) {
+    cluster_sync_all();                    // the leader's MMAs read the partner's shared memory and write its tensor memory
+    if (warp == 1) tmem_dealloc_pair<128>(tmem_acc);
+  } else {
+    if (warp == 1) tmem_dealloc<kLtTmemCols>(tmem_acc);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------- host
@@ -506,6 +565,43 @@ bool lt_pick(int N, int K, int sms, bool split, LtGemm* out, int max_bn) {
   return found;
 }
 
+// The same for CTA pairs: `pairs` units, column tile BN of the PAIR (each CTA holds BN/2 weight rows and 64 activation rows).
+// min_bn: 128 where the epilogue needs 32 columns per reader warp (SwiGLU), 64 otherwise.
+static bool lt_pick_pair(int N, int K, int pairs, bool split, int min_bn, LtGemm* out) {
+  if (K % 64 != 0) return false;
+  const int nkb = K / 64;
+  static const int max_s = [] { const char* e = getenv("VLG_LT_MAXS"); return e ? atoi(e) : 8; }();
+  double best = 1e30;
+  bool found = false;
+  for (int bn : {64, 128}) {
+    if (bn < min_bn || N % bn) continue;
+    const int tiles = N / bn;
+    if (tiles > pairs) continue;
+    int s0 = split ? pairs / tiles : 1;
+    if (s0 > nkb) s0 = nkb;
+    if (s0 > max_s) s0 = max_s;
+    const int kb_per = (nkb + s0 - 1) / s0;
+    const int S = (nkb + kb_per - 1) / kb_per;
+    double cost = (double)kb_per * (64 + bn / 2) * 128.0;                 // bytes through one SM's port
+    if (split) cost += 4.0 * 64.0 * bn * 4.0 + (double)S * 128 * N * 4.0 / (2 * pairs);
+    if (cost < best) {
+      best = cost;
+      found = true;
+      out->N = N; out->K = K; out->BN = bn; out->S = S; out->n_tiles = tiles; out->kb_per = kb_per;
+    }
+  }
+  return found;
+}
+
+// CTA pairs pay off when the activation slab is what fills the port: more than 64 rows.  VLG_LT_PAIR=0 keeps single CTAs (A/B).
+static bool lt_pair_plan(int rows, int dim, int hidden, int sms, LtGemm* wo, LtGemm* w13, LtGemm* w2, LtGemm* qkv) {
+  static const bool off = [] { const char* e = getenv("VLG_LT_PAIR"); return e && e[0] == '0'; }();
+  if (off || rows <= 64 || sms < 2 || (sms & 1)) return false;
+  const int pairs = sms / 2;
+  return lt_pick_pair(dim, dim, pairs, true, 64, wo) && lt_pick_pair(2 * hidden, dim, pairs, false, 128, w13) &&
+         lt_pick_pair(dim, hidden, pairs, true, 64, w2) && lt_pick_pair(3 * dim, dim, pairs, false, 64, qkv);
+}
+
 bool layer_tail_supported(int rows, int dim, int hidden) {
   static const bool off = [] { const char* e = getenv("VLG_LT"); return e && e[0] == '0'; }();
   if (off) return false;
@@ -528,6 +624,12 @@ size_t layer_tail_scratch_bytes(int max_rows, int dim, int hidden) {
       const size_t b = (size_t)t.S * rows * t.N * sizeof(float);
       if (b > worst) worst = b;
     }
+  LtGemm pw, p13, p2, pq;
+  if (lt_pair_plan(128, dim, hidden, sms, &pw, &p13, &p2, &pq))
+    for (const LtGemm* t : {&pw, &p2}) {
+      const size_t b = (size_t)t->S * rows * t->N * sizeof(float);
+      if (b > worst) worst = b;
+    }
   return worst + 1024;
 }
 
@@ -540,10 +642,13 @@ int launch_layer_tail(const LtLaunch& a, cudaStream_t st) {
   P.rows = a.rows; P.dim = a.dim; P.hidden = a.hidden;
   P.has_front = a.wo != nullptr;
   P.has_qkv = a.wqkv != nullptr;
-  lt_pick(a.dim, a.dim, sms, true, &P.g_wo);
-  lt_pick(2 * a.hidden, a.dim, sms, false, &P.g_w13);
-  lt_pick(a.dim, a.hidden, sms, true, &P.g_w2);
-  lt_pick(3 * a.dim, a.dim, sms, false, &P.g_qkv);
+  const bool pair = lt_pair_plan(a.rows, a.dim, a.hidden, sms, &P.g_wo, &P.g_w13, &P.g_w2, &P.g_qkv);
+  if (!pair) {
+    lt_pick(a.dim, a.dim, sms, true, &P.g_wo);
+    lt_pick(2 * a.hidden, a.dim, sms, false, &P.g_w13);
+    lt_pick(a.dim, a.hidden, sms, true, &P.g_w2);
+    lt_pick(3 * a.dim, a.dim, sms, false, &P.g_qkv);
+  }
   const LtGemm* gs[2] = {&P.g_wo, &P.g_w2};
   for (const LtGemm* g : gs)
     VLG_REQUIRE((size_t)g->S * a.rows * g->N * sizeof(float) <= a.part_bytes, "layer_tail: scratch too small (%zu bytes)", a.part_bytes);
@@ -564,7 +669,7 @@ int launch_layer_tail(const LtLaunch& a, cudaStream_t st) {
   // Activation tiles are loaded at their real height: a 128-row box over a 16-row tensor makes TMA zero-fill 14 KB of every
   // 16 KB tile, and the fill occupies the copy engine like real bytes do.  VLG_LT_FULLBOX=1 restores the padded box (A/B).
   static const bool full_box = [] { const char* e = getenv("VLG_LT_FULLBOX"); return e && e[0] == '1'; }();
-  const uint32_t a_rows = full_box ? 128u : (uint32_t)((a.rows + 7) / 8 * 8);
+  const uint32_t a_rows = pair ? 64u : full_box ? 128u : (uint32_t)((a.rows + 7) / 8 * 8);   // a pair's CTA loads 64 rows
   P.a_bytes = a_rows * 128u;
   // L2 prefetch budget per launch (MB of next-layer K + V).  OFF by default: measured on B200 (gpurun_out of round 2,
   // DESIGN.md 4.1) the attention kernel runs at the same speed from L2-resident K/V as from HBM (its shared-memory / issue
@@ -584,16 +689,25 @@ int launch_layer_tail(const LtLaunch& a, cudaStream_t st) {
   if (P.has_front) {
     if ((rc = make_tmap_bf16_2d(&tmAttn, a.attn, (uint64_t)a.rows, (uint64_t)a.dim, (uint64_t)a.dim * 2, a_rows, 64, true))) return rc;
     if ((rc = make_tmap_bf16_2d(&tmFfn, a.ffn, (uint64_t)a.rows, (uint64_t)a.hidden, (uint64_t)a.hidden * 2, a_rows, 64, true))) return rc;
-    if ((rc = make_tmap_bf16_2d(&tmWo, a.wo, (uint64_t)a.dim, (uint64_t)a.dim, (uint64_t)a.dim * 2, P.g_wo.BN, 64, true))) return rc;
-    if ((rc = make_tmap_bf16_2d(&tmW13, a.w13, (uint64_t)2 * a.hidden, (uint64_t)a.dim, (uint64_t)a.dim * 2, P.g_w13.BN, 64, true))) return rc;
-    if ((rc = make_tmap_bf16_2d(&tmW2, a.w2, (uint64_t)a.dim, (uint64_t)a.hidden, (uint64_t)a.hidden * 2, P.g_w2.BN, 64, true))) return rc;
+    if ((rc = make_tmap_bf16_2d(&tmWo, a.wo, (uint64_t)a.dim, (uint64_t)a.dim, (uint64_t)a.dim * 2, P.g_wo.BN >> (pair ? 1 : 0), 64, true))) return rc;
+    if ((rc = make_tmap_bf16_2d(&tmW13, a.w13, (uint64_t)2 * a.hidden, (uint64_t)a.dim, (uint64_t)a.dim * 2, P.g_w13.BN >> (pair ? 1 : 0), 64, true))) return rc;
+    if ((rc = make_tmap_bf16_2d(&tmW2, a.w2, (uint64_t)a.dim, (uint64_t)a.hidden, (uint64_t)a.hidden * 2, P.g_w2.BN >> (pair ? 1 : 0), 64, true))) return rc;
   }
   if (P.has_qkv)
-    if ((rc = make_tmap_bf16_2d(&tmWqkv, a.wqkv, (uint64_t)3 * a.dim, (uint64_t)a.dim, (uint64_t)a.dim * 2, P.g_qkv.BN, 64, true))) return rc;
+    if ((rc = make_tmap_bf16_2d(&tmWqkv, a.wqkv, (uint64_t)3 * a.dim, (uint64_t)a.dim, (uint64_t)a.dim * 2, P.g_qkv.BN >> (pair ? 1 : 0), 64, true))) return rc;
 
+  if (pair) {
+    auto kern = layer_tail_kernel<kLtStagesPair, kLtStageBytesPair, true>;
+    const int smem = lt_smem_bytes(kLtStagesPair, kLtStageBytesPair);
+    static PerDeviceOnce attr_once_pair;
+    VLG_CUDA(attr_once_pair([&] { return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); }));
+    VLG_CUDA(launch_kernel_cluster(kern, dim3(sms), dim3(kLtThreads), (size_t)smem, st, 2, tmAttn, tmXn, tmFfn, tmWo, tmW13, tmW2, tmWqkv, P));
+    VLG_LAUNCH_CHECK();
+    return VLG_OK;
+  }
   // ring layout by the widest column tile in use (see kLtStagesNarrow)
   const bool narrow = P.g_wo.BN <= 64 && P.g_w13.BN <= 64 && P.g_w2.BN <= 64 && P.g_qkv.BN <= 64;
-  auto kern = narrow ? layer_tail_kernel<kLtStagesNarrow, kLtStageBytesNarrow> : layer_tail_kernel<kLtStages, kLtStageBytesWide>;
+  auto kern = narrow ? layer_tail_kernel<kLtStagesNarrow, kLtStageBytesNarrow, false> : layer_tail_kernel<kLtStages, kLtStageBytesWide, false>;
   const int smem = narrow ? lt_smem_bytes(kLtStagesNarrow, kLtStageBytesNarrow) : lt_smem_bytes(kLtStages, kLtStageBytesWide);
   static PerDeviceOnce attr_once[2];
   VLG_CUDA(attr_once[narrow]([&] { return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); }));
