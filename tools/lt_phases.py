@@ -17,7 +17,8 @@ cond = torch.randint(0, 1000, (int(os.environ.get("VLG_PH_BATCH", "64")),)).cuda
 n_new = int(sys.argv[1]) if len(sys.argv) > 1 else 288
 names = {0: "start", 1: "pdl_wait", 2: "wo issued", 3: "bar", 4: "norm1", 5: "bar", 6: "w13 issued", 7: "bar", 8: "w2 issued",
          9: "bar", 10: "norm2", 11: "bar", 12: "qkv issued", 16: "wo acc", 17: "wo epi", 18: "w13 acc", 19: "w13 epi",
-         20: "w2 acc", 21: "w2 epi", 22: "qkv acc", 23: "qkv epi"}
+         20: "w2 acc", 21: "w2 epi", 22: "qkv acc", 23: "qkv epi",
+         24: "w13 epi: acc 0 read", 25: "w13 epi: acc 1 added", 26: "w13 epi: math done"}
 for rep in range(2):
     generate(m, cond, n_new, cfg_scale=4.0, temperature=1.0, top_k=2000, top_p=1.0, sample_logits=True, seed=rep)
     torch.cuda.synchronize()

@@ -120,6 +120,15 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&p);
 }
 
+// round two floats to bf16 and back with ONE packed conversion (cvt.rn.bf16x2.f32 -> F2FP, ALU-rate) instead of two scalar
+// F2F conversions, which share the 16-lane-per-clock pipe with MUFU: in the SwiGLU epilogue the scalar roundings alone were
+// ~1000 cycles per CTA.  Same round-to-nearest-even as rnd<__nv_bfloat16>.
+__device__ __forceinline__ void rnd2_bf16(float& a, float& b) {
+  const uint32_t p = pack_bf16(a, b);
+  a = bf16lo(p);
+  b = bf16hi(p);
+}
+
 // 128-bit streaming load that does not allocate in L1 (data read exactly once)
 __device__ __forceinline__ uint4 ldg_stream(const void* p) {
   uint4 r;

@@ -101,28 +101,37 @@ __device__ unsigned long long g_lt_ts[160 * 32];
 // from being scheduled, the wait is bounded (2 s of globaltimer) and ends in an error word in mapped host memory that the
 // host turns into VLG_ERR_STATE on its next call -- never in a trap that would poison the CUDA context.  Once the word is
 // set every later barrier of every CTA falls through at once, so a contended launch drains in seconds, not minutes.
+// Warp 0 (the TMA producer) is not part of the arrival: at the end of a GEMM phase it is still requesting the NEXT phase's
+// weight tiles (waiting for ring slots, ~13 TMA issues), and with a CTA-wide __syncthreads in front of the arrival one late
+// producer held back the whole grid (phase timeline: arrivals up to 1 us after the last epilogue store).  The workers (warps
+// 1..) synchronise among themselves, one of them arrives and polls, and the producer joins at the closing __syncthreads.
+constexpr int kLtWorkers = kLtThreads - 32;
+__device__ __forceinline__ void lt_workers_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kLtWorkers) : "memory"); }
+
 __device__ __forceinline__ void lt_grid_barrier(unsigned* ctr, unsigned& target, volatile unsigned* err) {
   target += gridDim.x;
   tc_fence_before();
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    // release: cumulative over the CTA's stores ordered before it by the bar.sync above (tools/micro/bar_bench.cu: the
-    // extra fences of the cooperative-groups recipe cost 0.25 us per barrier and add nothing to this pattern;
-    // tools/micro/bar_bench2.cu: moving the pollers off the counter's line onto flag lines is slower, 1.8-2.0 vs 1.25 us)
-    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
-    unsigned seen, spins = 0;
-    unsigned long long t0 = 0;
-    for (;;) {
-      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(ctr) : "memory");
-      if (seen >= target) break;
-      if ((++spins & 1023u) == 0) {
-        unsigned long long now;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-        if (t0 == 0) t0 = now;
-        if (err != nullptr && *err != 0) break;                       // somebody already gave up
-        if (now - t0 > 2000000000ull) {
-          if (err != nullptr) { *err = 1u; __threadfence_system(); }
-          break;
+  if (threadIdx.x >= 32) {
+    lt_workers_sync();                      // every global store of this CTA's phase is issued (the producer makes none)
+    if (threadIdx.x == 32) {
+      // release: cumulative over the workers' stores ordered before it by the bar.sync above (tools/micro/bar_bench.cu: the
+      // extra fences of the cooperative-groups recipe cost 0.25 us per barrier and add nothing to this pattern;
+      // tools/micro/bar_bench2.cu: moving the pollers off the counter's line onto flag lines is slower, 1.8-2.0 vs 1.25 us)
+      asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
+      unsigned seen, spins = 0;
+      unsigned long long t0 = 0;
+      for (;;) {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(ctr) : "memory");
+        if (seen >= target) break;
+        if ((++spins & 1023u) == 0) {
+          unsigned long long now;
+          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+          if (t0 == 0) t0 = now;
+          if (err != nullptr && *err != 0) break;                       // somebody already gave up
+          if (now - t0 > 2000000000ull) {
+            if (err != nullptr) { *err = 1u; __threadfence_system(); }
+            break;
+          }
         }
       }
     }
@@ -318,6 +327,19 @@ __device__ __forceinline__ void lt_gemm_phase(const LtGemm& G, const TensorMap* 
       constexpr uint32_t kAcc2 = PAIR ? 64u : 128u;               // TMEM column distance of the second issuer's accumulator
       const uint32_t lane_base = tmem_acc + (static_cast<uint32_t>(quad * 32) << 16);
       const bool two = u.nkb > 1;            // the second issuer's accumulator holds the odd k-blocks
+      // RoPE: the cache position and the first chunk's (cos, sin) pairs are two dependent global loads; request them while
+      // the main loop still runs instead of after the accumulator is ready
+      int rope_pos = 0;
+      float2 rope_cs[8];
+      if constexpr (MODE == EPI_QKV_ROPE) {
+        rope_pos = E.pos_ptr ? *E.pos_ptr : E.pos_imm;
+        const int n = u.n0 + cbase + half * 16, sec = n / E.dim, cc = n - sec * E.dim, dd = cc % E.D;
+        if (sec < 2) {
+          const float2* tab = reinterpret_cast<const float2*>(E.rope) + (size_t)rope_pos * (E.D >> 1) + (dd >> 1);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) rope_cs[i] = tab[i];
+        }
+      }
       mbar_wait(&sm.acc_ready, acc_uses & 1);
       tc_fence_after();
       if (threadIdx.x == 64) LT_TS_AT(ts_slot);
@@ -337,21 +359,37 @@ __device__ __forceinline__ void lt_gemm_phase(const LtGemm& G, const TensorMap* 
           float v[32];
           tmem_ld16(lane_base + c, v);
           tmem_ld16(lane_base + c + 16, v + 16);
+          if (threadIdx.x == 64) LT_TS_AT(24);
           if (two) { lt_add_acc16(lane_base + kAcc2 + c, v); lt_add_acc16(lane_base + kAcc2 + c + 16, v + 16); }
+          if (threadIdx.x == 64) LT_TS_AT(25);
           if (r < P.rows) {
             float o[16];
+            // one branch around two straight-line loops: with the choice made per element ptxas keeps the 16 independent
+            // MUFU chains in sequence (measured: 2.0 us for this block, most of the phase's epilogue)
+            if (P.fast_silu) {       // 2-3 ulp of fp32 before the bf16 rounding of silu (2^-9 relative)
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const float a = rnd<__nv_bfloat16>(v[2 * i]), b = rnd<__nv_bfloat16>(v[2 * i + 1]);
-              // fast form: 2-3 ulp of fp32 before the bf16 rounding of silu (2^-9 relative), instead of ~40 instructions
-              const float sl = P.fast_silu ? __fdividef(a, 1.0f + __expf(-a)) : silu_f(a);
-              o[i] = __fmul_rn(rnd<__nv_bfloat16>(sl), b);
+              for (int i = 0; i < 16; i += 2) {
+                float a0 = v[2 * i], b0 = v[2 * i + 1], a1 = v[2 * i + 2], b1 = v[2 * i + 3];
+                rnd2_bf16(a0, b0);
+                rnd2_bf16(a1, b1);
+                float s0 = __fdividef(a0, 1.0f + __expf(-a0)), s1 = __fdividef(a1, 1.0f + __expf(-a1));
+                rnd2_bf16(s0, s1);
+                o[i] = __fmul_rn(s0, b0);
+                o[i + 1] = __fmul_rn(s1, b1);
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const float a = rnd<__nv_bfloat16>(v[2 * i]), b = rnd<__nv_bfloat16>(v[2 * i + 1]);
+                o[i] = __fmul_rn(rnd<__nv_bfloat16>(silu_f(a)), b);
+              }
             }
+            if (threadIdx.x == 64) LT_TS_AT(26);
             stg256_bf16x16(static_cast<__nv_bfloat16*>(E.out) + (size_t)r * E.ld_out + ((u.n0 + cbase + c) >> 1), o);
           }
         }
       } else {                                         // EPI_QKV_ROPE on 16 columns (a quarter head): gpt.py:215-227, 423-433, 177-185
-        const int pos = E.pos_ptr ? *E.pos_ptr : E.pos_imm;
+        const int pos = rope_pos;
         for (int c = half * 16; c < ncol; c += 16 * kLtHalves) {
           float v[16];
           tmem_ld16(lane_base + c, v);
@@ -363,8 +401,9 @@ __device__ __forceinline__ void lt_gemm_phase(const LtGemm& G, const TensorMap* 
               const float2* tab = reinterpret_cast<const float2*>(E.rope) + (size_t)pos * (E.D >> 1) + (dd >> 1);
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
-                const float2 cs = tab[i];
-                const float x0 = rnd<__nv_bfloat16>(v[2 * i]), x1 = rnd<__nv_bfloat16>(v[2 * i + 1]);
+                const float2 cs = c == half * 16 ? rope_cs[i] : tab[i];
+                float x0 = v[2 * i], x1 = v[2 * i + 1];
+                rnd2_bf16(x0, x1);
                 o[2 * i] = __fsub_rn(__fmul_rn(x0, cs.x), __fmul_rn(x1, cs.y));
                 o[2 * i + 1] = __fadd_rn(__fmul_rn(x1, cs.x), __fmul_rn(x0, cs.y));
               }
@@ -390,7 +429,8 @@ __device__ __forceinline__ void lt_gemm_phase(const LtGemm& G, const TensorMap* 
 // h <- T(h + T(sum of partials))  (when G != null), then xn <- T(T(h * rsqrt(mean(h^2) + eps)) * w): one row per CTA
 template <int ST>
 __device__ __forceinline__ void lt_norm_phase(const LtGemm* G, const __nv_bfloat16* w, const LtParams& P, LtSmem<ST>& sm) {
-  const int nvec = P.dim / 8, t = threadIdx.x;
+  if (threadIdx.x < 32) return;            // the producer warp keeps requesting weight tiles; the workers own the row phases
+  const int nvec = P.dim / 8, t = threadIdx.x - 32;
   const bool active = t < nvec;
   float g8[8];
   if (active) load8<__nv_bfloat16>(w + t * 8, g8);
@@ -406,24 +446,34 @@ __device__ __forceinline__ void lt_norm_phase(const LtGemm* G, const __nv_bfloat
         float acc[8];
         lt_reduce8(P.part, G->S, (size_t)P.rows * G->N, (size_t)r * G->N + t * 8, acc);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) hn[i] = rnd<__nv_bfloat16>(__fadd_rn(hn[i], rnd<__nv_bfloat16>(acc[i])));
+        for (int i = 0; i < 8; i += 2) {
+          rnd2_bf16(acc[i], acc[i + 1]);
+          hn[i] = __fadd_rn(hn[i], acc[i]);
+          hn[i + 1] = __fadd_rn(hn[i + 1], acc[i + 1]);
+          rnd2_bf16(hn[i], hn[i + 1]);
+        }
         store8<__nv_bfloat16>(hp, hn);
       }
 #pragma unroll
       for (int i = 0; i < 8; ++i) ss = __fadd_rn(ss, __fmul_rn(hn[i], hn[i]));
     }
     ss = warp_sum(ss);
-    __syncthreads();                                   // previous row's readers of sm.red are done
+    lt_workers_sync();                                 // previous row's readers of sm.red are done
     if ((t & 31) == 0) sm.red[t >> 5] = ss;
-    __syncthreads();
+    lt_workers_sync();
     float tot = 0.f;
 #pragma unroll
-    for (int i = 0; i < kLtThreads / 32; ++i) tot += sm.red[i];
+    for (int i = 0; i < kLtWorkers / 32; ++i) tot += sm.red[i];
     const float rs = rsqrtf(__fdiv_rn(tot, (float)P.dim) + P.eps);
     if (active) {
       float o[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) o[i] = __fmul_rn(rnd<__nv_bfloat16>(__fmul_rn(hn[i], rs)), g8[i]);
+      for (int i = 0; i < 8; i += 2) {
+        float y0 = __fmul_rn(hn[i], rs), y1 = __fmul_rn(hn[i + 1], rs);
+        rnd2_bf16(y0, y1);
+        o[i] = __fmul_rn(y0, g8[i]);
+        o[i + 1] = __fmul_rn(y1, g8[i + 1]);
+      }
       store8<__nv_bfloat16>(P.xn + (size_t)r * P.dim + t * 8, o);
     }
   }
@@ -605,7 +655,7 @@ static bool lt_pair_plan(int rows, int dim, int hidden, int sms, LtGemm* wo, LtG
 bool layer_tail_supported(int rows, int dim, int hidden) {
   static const bool off = [] { const char* e = getenv("VLG_LT"); return e && e[0] == '0'; }();
   if (off) return false;
-  if (rows <= 0 || rows > 128 || dim % 64 != 0 || hidden % 64 != 0 || dim / 8 > kLtThreads) return false;
+  if (rows <= 0 || rows > 128 || dim % 64 != 0 || hidden % 64 != 0 || dim / 8 > kLtThreads - 32) return false;
   const int sms = num_sms();
   LtGemm t;
   return lt_pick(dim, dim, sms, true, &t) && lt_pick(2 * hidden, dim, sms, false, &t) && lt_pick(dim, hidden, sms, true, &t) &&
