@@ -199,7 +199,7 @@ def layer_tail_roofline(model, dev, rows, new_tokens, peak_gbs, src):
             "frac": round(achieved / peak_gbs, 4), "traffic": traffic, "peak_source": src, "avg_launch_us": round(us, 2),
             "launches_timed": reps * (cfg.n_layer + 1), "algorithmic_bytes_per_launch": w_bytes + act_bytes,
             "note": "one launch per layer for everything between two attentions; streams the layer's weights once, but is "
-                    "bounded by the per-SM L2 port (102 MB L2->SM per launch) and five grid barriers, not by HBM (DESIGN.md 4)"}
+                    "paced by the SM's L2 port (CTA pairs halve the activation bytes through it) and by six dependent exchanges through L2 with five grid barriers, not by HBM (DESIGN.md 4.1)"}
 
 
 

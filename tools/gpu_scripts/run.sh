@@ -7,6 +7,7 @@
 #   vq      VQ index search: default + variants
 #   micro   microbenchmarks behind DESIGN.md 4.1 (build them first: see the header of each .cu)
 #   prof    ncu evidence: launch list, full captures of the step kernels and the VQ score kernel
+#   pair    cfg-2 with and without CTA pairs in the layer tail (same box), phase timeline
 #   switches  decode parity tests under every A/B switch
 set -u
 mkdir -p gpurun_out
@@ -40,8 +41,12 @@ prof)
   unset VLG_PROFILE_STEP
   python tools/vq_bench.py > gpurun_out/vq_plain.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:vq_score -c 1 -f -o gpurun_out/vq_score python tools/vq_bench.py > gpurun_out/vq_ncu.log 2>&1
   echo "vq capture rc=$?" ;;
+pair)
+  timeout 300 python bench.py --steps 3 --warmup 2 --skip-extras 2>/dev/null | cut -c1-150
+  VLG_LT_PAIR=0 timeout 300 python bench.py --steps 3 --warmup 2 --skip-extras 2>/dev/null | cut -c1-150 | sed 's/^/PAIR=0 /'
+  timeout 200 python tools/lt_phases.py 288 2>&1 | tail -24 | tee gpurun_out/lt_phases.txt ;;
 switches)
-  for sw in VLG_LT=0 VLG_LT_V=2 VLG_ATTN=generic VLG_PDL=0 VLG_STEPPED_PREFILL=1 VLG_NO_GRAPH=1 VLG_FUSED_NORM=1; do
+  for sw in VLG_LT=0 VLG_LT_PAIR=0 VLG_LT_V=2 VLG_ATTN=generic VLG_PDL=0 VLG_STEPPED_PREFILL=1 VLG_NO_GRAPH=1 VLG_FUSED_NORM=1; do
     env $sw timeout 600 python -m pytest tests/test_gpu_decode.py -q -x 2>&1 | tail -1 | cut -c1-120 | sed "s/^/$sw: /"
   done ;;
 *) echo "unknown recipe $what" ;;
