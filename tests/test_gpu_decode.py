@@ -167,11 +167,13 @@ def test_gptl_cfg2_full_size_bf16():
 
 
 @pytest.mark.parametrize("name,n_layer,B", [("GPT-B", 3, 4), ("GPT-XL", 2, 8), ("GPT-XXL", 2, 32), ("GPT-1B", 2, 64),
-                                            ("GPT-B", 2, 80)])   # 160 rows: beyond the layer-tail kernel, per-op kernels
+                                            ("GPT-XL", 2, 48),    # 96 rows: CTA pairs with a ragged second half (32 live rows)
+                                            ("GPT-XXL", 2, 64),   # 128 rows: CTA pairs at d = 1536 (24 k-blocks through 13 stages)
+                                            ("GPT-B", 2, 80)])    # 160 rows: beyond the layer-tail kernel, per-op kernels
 def test_layer_tail_geometries_bf16(name, n_layer, B):
     """The persistent layer-tail kernel (split-K tile shapes, ring wrap-around, row phases) at the widths of the other
-    registry entries -- d = 768 / 1280 / 1536 / 2048, hidden 2048 / 3584 / 4096 / 5632, 8..128 cache rows -- on a few
-    layers: teacher-forced bf16 logits against the oracle on the same GPU."""
+    registry entries -- d = 768 / 1280 / 1536 / 2048, hidden 2048 / 3584 / 4096 / 5632, 8..128 cache rows (single CTAs up to 64
+    rows, CTA pairs above) -- on a few layers: teacher-forced bf16 logits against the oracle on the same GPU."""
     kw = dict(O.NAMED[name])
     kw["n_layer"] = n_layer
     geo = O.Geometry(block_size=64, vocab_size=1024, **kw)

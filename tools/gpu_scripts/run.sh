@@ -46,7 +46,7 @@ pair)
   VLG_LT_PAIR=0 timeout 300 python bench.py --steps 3 --warmup 2 --skip-extras 2>/dev/null | cut -c1-150 | sed 's/^/PAIR=0 /'
   timeout 200 python tools/lt_phases.py 288 2>&1 | tail -24 | tee gpurun_out/lt_phases.txt ;;
 switches)
-  for sw in VLG_LT=0 VLG_LT_PAIR=0 VLG_LT_V=2 VLG_ATTN=generic VLG_PDL=0 VLG_STEPPED_PREFILL=1 VLG_NO_GRAPH=1 VLG_FUSED_NORM=1; do
+  for sw in VLG_LT=0 VLG_LT_PAIR=0 VLG_ATTN=generic VLG_PDL=0 VLG_STEPPED_PREFILL=1 VLG_NO_GRAPH=1 VLG_FUSED_NORM=1; do
     env $sw timeout 600 python -m pytest tests/test_gpu_decode.py -q -x 2>&1 | tail -1 | cut -c1-120 | sed "s/^/$sw: /"
   done ;;
 *) echo "unknown recipe $what" ;;

@@ -22,27 +22,13 @@ names = {0: "start", 1: "pdl_wait", 2: "wo issued", 3: "bar", 4: "norm1", 5: "ba
 for rep in range(2):
     generate(m, cond, n_new, cfg_scale=4.0, temperature=1.0, top_k=2000, top_p=1.0, sample_logits=True, seed=rep)
     torch.cuda.synchronize()
-v2 = os.environ.get("VLG_LT_V", "1") == "2"
-NS = 64 if v2 else 32
+NS = 32
 ts = (C.c_ulonglong * (160 * NS))()
-v2_ = os.environ.get("VLG_LT_V", "2") == "2"
-if v2:   # layer_tail2.cu: per (stage, group) stamps of the epilogue / row groups (E) and of the producer seeing its input (P)
-    L.check(lib.vlg_debug_lt2_timestamps(ts))
-    st = ["wo", "norm1", "w13", "w2", "norm2", "qkv"]
-    names = {0: "start", 1: "pdl_wait"}
-    for i, n in enumerate(st):
-        for g in range(2):
-            names[2 + 2 * i + g] = f"E{g} {n} done"
-            names[16 + 2 * i + g] = f"P sees {n}[{g}]"
-    for g in range(2):
-        for i, n in enumerate(["M acc free", "M first tiles", "M last mma", "E acc ready", "E stored", "E signalled", "P first A", "P last A"]):
-            names[32 + 8 * g + i] = f"w13[{g}] {n}"
-else:
-    L.check(lib.vlg_debug_lt_timestamps(ts))
+L.check(lib.vlg_debug_lt_timestamps(ts))
 t = np.array(ts, dtype=np.int64).reshape(160, NS)[:148].astype(np.float64)
 t0 = t[:, 1][t[:, 1] > 0].min()          # first CTA past pdl_wait
 print(f"new_tokens {n_new}; times in us relative to the first CTA leaving pdl_wait; min / median / max over CTAs that have the stamp")
-order = sorted(names, key=lambda k: np.median(t[:, k][t[:, k] > 0]) if (t[:, k] > 0).any() else 0) if v2 else sorted(names)
+order = sorted(names)
 for k in order:
     col = t[:, k]
     col = col[col > 0] - t0

@@ -668,7 +668,7 @@ size_t layer_tail_scratch_bytes(int max_rows, int dim, int hidden) {
   size_t worst = 0;
   const int shapes[2][2] = {{dim, dim}, {dim, hidden}};   // wo and w2 are the split-K GEMMs
   for (auto& sh : shapes)
-    for (int max_bn : {64, 128}) {          // layer_tail2.cu caps the column tile at 64 and may end up with another split count
+    for (int max_bn : {64, 128}) {
       LtGemm t;
       if (!lt_pick(sh[0], sh[1], sms, true, &t, max_bn)) continue;
       const size_t b = (size_t)t.S * rows * t.N * sizeof(float);
@@ -684,7 +684,6 @@ size_t layer_tail_scratch_bytes(int max_rows, int dim, int hidden) {
 }
 
 int launch_layer_tail(const LtLaunch& a, cudaStream_t st) {
-  if (layer_tail2_supported(a.rows, a.dim, a.hidden)) return launch_layer_tail2(a, st);   // VLG_LT_V=1 keeps this file's kernel
   VLG_REQUIRE(layer_tail_supported(a.rows, a.dim, a.hidden), "layer_tail: unsupported shape rows=%d dim=%d hidden=%d", a.rows, a.dim, a.hidden);
   VLG_REQUIRE(a.wo || a.wqkv, "layer_tail: nothing to do");
   const int sms = num_sms();

@@ -1,5 +1,4 @@
-// Pieces shared by the two layer-tail kernels (layer_tail.cu: lock-step phases with grid barriers; layer_tail2.cu: two row
-// groups pipelined through the stages by decoupled actors).
+// Layer-tail kernel: unit geometry and memory helpers (layer_tail.cu).
 #pragma once
 #include <stdlib.h>
 
@@ -82,9 +81,6 @@ __device__ __forceinline__ void lt_reduce8(const float* part, int S, size_t spli
 // Tile shape and split count per GEMM (host): see layer_tail.cu.  max_bn caps the column tile.
 bool lt_pick(int N, int K, int sms, bool split, LtGemm* out, int max_bn = 128);
 
-// layer_tail2.cu
-bool layer_tail2_supported(int rows, int dim, int hidden);
-int launch_layer_tail2(const LtLaunch& a, cudaStream_t st);
-constexpr int kLtCounterBytes = 2048;     // counter region both kernels share (zero between launches)
+constexpr int kLtCounterBytes = 2048;     // grid-barrier / exit counter region (zero between launches)
 
 }  // namespace vlg
