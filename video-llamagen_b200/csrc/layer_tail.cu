@@ -643,10 +643,33 @@ static bool lt_pick_pair(int N, int K, int pairs, bool split, int min_bn, LtGemm
   return found;
 }
 
+// The grid barriers need every cluster resident at once: ask the driver how many 2-CTA clusters of the pair kernel the device
+// holds (GPC shapes or a partitioned device can strand SMs) and use pairs only when that covers the whole grid.
+static bool lt_pairs_fit(int sms) {
+  static int cached[kMaxDevices] = {};                      // 0 unknown, 1 yes, -1 no
+  int& c = cached[current_device()];
+  if (c == 0) {
+    auto kern = layer_tail_kernel<kLtStagesPair, kLtStageBytesPair, true>;
+    const int smem = lt_smem_bytes(kLtStagesPair, kLtStageBytesPair);
+    int n = 0;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(sms); cfg.blockDim = dim3(kLtThreads); cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    const bool ok = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) == cudaSuccess &&
+                    cudaOccupancyMaxActiveClusters(&n, kern, &cfg) == cudaSuccess && 2 * n >= sms;
+    if (!ok) cudaGetLastError();
+    c = ok ? 1 : -1;
+  }
+  return c > 0;
+}
+
 // CTA pairs pay off when the activation slab is what fills the port: more than 64 rows.  VLG_LT_PAIR=0 keeps single CTAs (A/B).
 static bool lt_pair_plan(int rows, int dim, int hidden, int sms, LtGemm* wo, LtGemm* w13, LtGemm* w2, LtGemm* qkv) {
   static const bool off = [] { const char* e = getenv("VLG_LT_PAIR"); return e && e[0] == '0'; }();
-  if (off || rows <= 64 || sms < 2 || (sms & 1)) return false;
+  if (off || rows <= 64 || sms < 2 || (sms & 1) || !lt_pairs_fit(sms)) return false;
   const int pairs = sms / 2;
   return lt_pick_pair(dim, dim, pairs, true, 64, wo) && lt_pick_pair(2 * hidden, dim, pairs, false, 128, w13) &&
          lt_pick_pair(dim, hidden, pairs, true, 64, w2) && lt_pick_pair(3 * dim, dim, pairs, false, 64, qkv);
