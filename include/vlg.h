@@ -202,6 +202,66 @@ int vlg_generate(vlg_ctx* ctx, const vlg_generate_params* p, const void* cond_de
 int vlg_generate_t2v(vlg_ctx* ctx, const vlg_generate_params* p, const void* cond_dev, const void* uncond_dev,
                      const uint8_t* emb_masks_dev, void* latents_dev, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Diffusion-head token sampler -- replaces DiffLoss.sample (autoregressive/models/diffloss.py:35-52):
+ * the `steps`-long p_sample_loop (diffusion/gaussian_diffusion.py:376-517, respaced by diffusion/respace.py:63-129) over
+ * SimpleMLPAdaLN (diffloss.py:151-247), eps-prediction with LEARNED_RANGE variance (diffusion/__init__.py:11-47), fp32.
+ * Call site in the reference: generate_video_diff.py:88-90 and :130-132 (one call per generated token).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+  int C;      /* target_channels: width of the latent being sampled (vae_embed_dim, 8 for the reference's VAE); <= 16 */
+  int W;      /* model_channels (diffloss_w, 1024): 128, 256, 512, 768 or 1024 */
+  int Z;      /* z_channels: width of the conditioning vector (the trunk's dim) */
+  int depth;  /* residual blocks (diffloss_d, 3) */
+  int steps;  /* respaced sampling steps (num_sampling_steps, 100) */
+} vlg_diff_geometry;
+
+/* all fp32 device pointers in nn.Linear layout [out, in]; names = state_dict keys under `net.` */
+typedef struct {
+  const float *ln_w, *ln_b;   /* res_blocks.b.in_ln.{weight,bias}            [W]       */
+  const float *w1, *b1;       /* res_blocks.b.mlp.0.{weight,bias}            [W, W], [W] */
+  const float *w2, *b2;       /* res_blocks.b.mlp.2.{weight,bias}            [W, W], [W] */
+  const float *ada_w, *ada_b; /* res_blocks.b.adaLN_modulation.1.{weight,bias} [3W, W], [3W] */
+} vlg_diff_block;
+
+typedef struct {
+  const float *time_w0, *time_b0;         /* time_embed.mlp.0  [W, 256], [W] */
+  const float *time_w1, *time_b1;         /* time_embed.mlp.2  [W, W], [W] */
+  const float *cond_w, *cond_b;           /* cond_embed        [W, Z], [W] */
+  const float *in_w, *in_b;               /* input_proj        [W, C], [W] */
+  const vlg_diff_block* blocks;           /* [depth] (host array, copied) */
+  const float *final_ada_w, *final_ada_b; /* final_layer.adaLN_modulation.1 [2W, W], [2W] */
+  const float *final_w, *final_b;         /* final_layer.linear [2C, W], [2C] */
+} vlg_diff_weights;
+
+typedef struct vlg_diff vlg_diff;
+
+size_t vlg_diff_workspace_bytes(const vlg_diff_geometry* g, int max_rows);   /* 0 when the geometry is unsupported */
+
+/* timestep_map_host int32 [steps]: original timestep of respaced step i (respace.py:77-85).
+ * tables_host fp32 [6][steps], the float64 tables of gaussian_diffusion.py:153-201 rounded to fp32 as _extract_into_tensor
+ * does (:865-877): sqrt_recip_alphas_cumprod, sqrt_recipm1_alphas_cumprod, posterior_mean_coef1, posterior_mean_coef2,
+ * posterior_log_variance_clipped, log(betas).  Both are schedule constants the caller derives on the host, as the
+ * reference does in numpy.  Weight pointers are borrowed and must outlive the handle; workspace_dev is 256-byte aligned.
+ * Computes the model's timestep-embedding table on the device and synchronises once.                              */
+int vlg_diff_create(const vlg_diff_geometry* g, const vlg_diff_weights* w, const int32_t* timestep_map_host,
+                    const float* tables_host, int max_rows, void* workspace_dev, size_t workspace_bytes, vlg_diff** out);
+void vlg_diff_destroy(vlg_diff* d);
+
+/* One DiffLoss.sample call: z_dev fp32 [rows, Z] -> out_dev fp32 [rows, C].
+ * cfg_scale == 1: plain sampling.  cfg_scale != 1: forward_with_cfg (diffloss.py:237-247) -- rows [0, rows/2) are the
+ * conditional, [rows/2, rows) the unconditional copies; both halves are fed the first half's sample, eps is mixed
+ * uncond + cfg_scale * (cond - uncond), every row keeps its own variance output and its own noise.
+ * noise_dev fp32 [rows, C]: the start sample (the caller duplicates it across the halves under guidance, as
+ * diffloss.py:38-39 does), or NULL to draw it in-kernel (Philox4x32-10 keyed by seed/offset, duplicated likewise).
+ * step_noise_dev fp32 [steps, rows, C]: entry i is the draw added at loop index i (i runs steps-1 .. 0; index 0 is
+ * never used, gaussian_diffusion.py:413-415), or NULL to draw in-kernel.  No host synchronisation.                */
+int vlg_diff_sample(vlg_diff* d, const float* z_dev, int rows, float temperature, float cfg_scale, const float* noise_dev,
+                    const float* step_noise_dev, uint64_t seed, uint64_t offset, float* out_dev, void* stream);
+
+/* Synchronises `stream` and reports (VLG_ERR_STATE) whether a launch since the last check gave up in a grid barrier. */
+int vlg_diff_check(vlg_diff* d, void* stream);
+
 /* Measurement only: register-resident FP32 FMA loop on every SM (variant 0: FFMA, 1: packed FFMA2); the caller times
  * it with events.  *flops_out = floating-point operations of the launch.  The roofline denominator of vlg_vq_argmin. */
 int vlg_debug_fp32_fma_peak(int variant, int iters, float* out_dev, long long* flops_out, void* stream);

@@ -74,12 +74,13 @@ def _shim_ipdb():
 _cache = {}
 
 
-def load(video=False):
+def load(video=False, diff=False):
     """Return a namespace with the reference's hot-path modules.
 
-    .gpt / .generate / .vq_model always; .gpt_video when ``video=True``.
+    .gpt / .generate / .vq_model always; .gpt_video when ``video=True``; .diffloss, .gpt_video_diff and
+    .generate_video_diff (the diffusion-head sampler) when ``diff=True``.
     """
-    key = bool(video)
+    key = (bool(video), bool(diff))
     if key in _cache:
         return _cache[key]
     if not available():
@@ -98,5 +99,23 @@ def load(video=False):
             dummy.VAE_models = {}
             sys.modules["tokenizer.tokenizer_image.vae_model"] = dummy
             ns.gpt_video = importlib.import_module("autoregressive.models.gpt_video")
+        if diff:
+            for name in ("ftfy", "bs4", "decord", "diffusers", "diffusers.utils",
+                         "matplotlib", "matplotlib.pyplot"):
+                sys.modules.setdefault(name, mock.MagicMock())
+            if "tokenizer.tokenizer_image.vae_model" not in sys.modules:
+                dummy = types.ModuleType("tokenizer.tokenizer_image.vae_model")
+                dummy.VAE_models = {}
+                sys.modules["tokenizer.tokenizer_image.vae_model"] = dummy
+            # gpt_video_diff.py:27 does a bare ``from diffloss import DiffLoss``: its own directory must be importable
+            models_dir = os.path.join(root(), "autoregressive", "models")
+            sys.path.insert(0, models_dir)
+            try:
+                ns.diffloss = importlib.import_module("diffloss")
+                ns.gpt_video_diff = importlib.import_module("autoregressive.models.gpt_video_diff")
+                ns.generate_video_diff = importlib.import_module("autoregressive.models.generate_video_diff")
+            finally:
+                sys.path.remove(models_dir)
+                sys.modules.pop("diffloss", None)
     _cache[key] = ns
     return ns

@@ -43,15 +43,17 @@ def test_binding_table_matches_header(built):
 def test_struct_sizes_match_the_c_side(built, tmp_path):
     """Compile a tiny C program against vlg.h and compare sizeof() with the ctypes mirrors."""
     src = tmp_path / "sz.c"
-    src.write_text('#include <stdio.h>\n#include "vlg.h"\nint main(){printf("%zu %zu %zu %zu %zu\\n",'
+    src.write_text('#include <stdio.h>\n#include "vlg.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu\\n",'
                    'sizeof(vlg_sample_params),sizeof(vlg_geometry),sizeof(vlg_layer_weights),sizeof(vlg_weights),'
-                   'sizeof(vlg_generate_params));return 0;}\n')
+                   'sizeof(vlg_generate_params),sizeof(vlg_diff_geometry),sizeof(vlg_diff_block),sizeof(vlg_diff_weights));'
+                   'return 0;}\n')
     exe = tmp_path / "sz"
     subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
     sizes = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True).stdout.split()]
     import ctypes as C
     assert sizes == [C.sizeof(built.SampleParams), C.sizeof(built.Geometry), C.sizeof(built.LayerWeights),
-                     C.sizeof(built.Weights), C.sizeof(built.GenerateParams)]
+                     C.sizeof(built.Weights), C.sizeof(built.GenerateParams), C.sizeof(built.DiffGeometry),
+                     C.sizeof(built.DiffBlock), C.sizeof(built.DiffWeights)]
 
 
 def test_sass_is_blackwell_native():

@@ -14,6 +14,7 @@
 //    with the noise either supplied by the caller (parity tests) or drawn in-kernel from Philox4x32-10.
 #include "common.cuh"
 #include "kernels.h"
+#include "philox.cuh"
 
 namespace vlg {
 
@@ -24,18 +25,6 @@ __device__ __forceinline__ uint32_t order_key(float f) {  // ascending uint orde
   return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
 }
 
-__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
-  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
-#pragma unroll
-  for (int i = 0; i < 10; ++i) {
-    uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
-    uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
-    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
-    key.x += W0;
-    key.y += W1;
-  }
-  return ctr;
-}
 __device__ __forceinline__ float exp1_from_bits(uint32_t x) {  // Exp(1) draw, u in (0,1)
   float u = ((float)(x >> 8) + 0.5f) * (1.0f / 16777216.0f);
   return -logf(u);

@@ -38,6 +38,20 @@ class GenerateParams(C.Structure):
                 ("seed", C.c_uint64)]
 
 
+class DiffGeometry(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("C", "W", "Z", "depth", "steps")]
+
+
+class DiffBlock(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("ln_w", "ln_b", "w1", "b1", "w2", "b2", "ada_w", "ada_b")]
+
+
+class DiffWeights(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("time_w0", "time_b0", "time_w1", "time_b1", "cond_w", "cond_b", "in_w", "in_b")] + \
+               [("blocks", C.POINTER(DiffBlock))] + \
+               [(n, C.c_void_p) for n in ("final_ada_w", "final_ada_b", "final_w", "final_b")]
+
+
 _P, _I, _I64, _SZ, _F = C.c_void_p, C.c_int, C.c_int64, C.c_size_t, C.c_float
 
 # name -> (restype, argtypes): exactly the symbols include/vlg.h declares
@@ -61,6 +75,11 @@ SIGNATURES = {
     "vlg_generate": (_I, [_P, C.POINTER(GenerateParams), _P, _P, _P, _P, _P]),
     "vlg_generate_t2v": (_I, [_P, C.POINTER(GenerateParams), _P, _P, _P, _P, _P]),
     "vlg_generate_c2i_host": (_I, [_P, C.POINTER(GenerateParams), _P, _P, _P]),
+    "vlg_diff_workspace_bytes": (_SZ, [C.POINTER(DiffGeometry), _I]),
+    "vlg_diff_create": (_I, [C.POINTER(DiffGeometry), C.POINTER(DiffWeights), _P, _P, _I, _P, _SZ, C.POINTER(_P)]),
+    "vlg_diff_destroy": (None, [_P]),
+    "vlg_diff_sample": (_I, [_P, _P, _I, _F, _F, _P, _P, C.c_uint64, C.c_uint64, _P, _P]),
+    "vlg_diff_check": (_I, [_P, _P]),
     "vlg_rmsnorm": (_I, [_P, _P, _P, _I, _I, _F, _I, _P]),
     "vlg_linear": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "vlg_attn_decode": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _I, _I, _I, _P, _SZ, _P]),
