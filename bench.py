@@ -13,8 +13,9 @@ full generate() over one batch: prefill + 575 graph-replayed decode steps.
               timed alone with CUDA events on their stream); the other one and the whole-step figure ride along
   cpu_baseline  the oracle port (reference algorithm restated, oracle/ar_decode.py) on this host's cores, bounded sample
   extras      (N = 1 only) the other BASELINE configs at full size -- cfg3 (GPT-XXL shard), cfg4_b8 (GPT-XL t2v), cfg5_vq
-              (1 M-latent index search against the measured FP32 FMA peak) -- the reference algorithm in bf16 on this GPU
-              (gpu_eager_baseline) and the Python-driven decode_n_tokens loop
+              (1 M-latent index search against the measured FP32 FMA peak) -- decode_code, diff_head (the diffusion-head
+              token sampler beside its eager port), the reference algorithm in bf16 on this GPU (gpu_eager_baseline) and
+              the Python-driven decode_n_tokens loop
 
 N > 1 (torchrun, one rank per GPU): every rank decodes its own 64-sample shard of a 64*N global batch (weak scaling),
 no collective inside the loop, one NCCL all_gather of the int32 code indices per step inside the timed region.
@@ -297,6 +298,44 @@ def extra_cfg5(dev):
             "peak": max(peak.values()), "unit": "TFLOP/s", "frac": round(tf / max(peak.values()), 4),
             "peak_source": "measured here: register-resident FMA loop", "peaks": peak,
             "algorithmic_flops": 2 * n * 16384 * 8}}
+
+
+def extra_diff_head(dev, rows=1):
+    """Diffusion-head token sampler in the configuration the reference ships (GPT-1B trunk: z of 2048,
+    head width 1024, depth 3, 100 sampling steps, batch 1, no guidance; scripts/sample/sample_t2v_diff.bash): one
+    DiffLoss.sample per generated token.  Latency-bound (a chain of 700 dependent layers per token); reported beside the
+    oracle port of the same call through torch library kernels on the same GPU."""
+    import time
+    import torch
+    from vlg.diffloss import DiffLoss
+    from oracle import diffusion as D
+    torch.manual_seed(0)
+    head = DiffLoss(target_channels=8, z_channels=2048, depth=3, width=1024, num_sampling_steps="100").eval()
+    for m in head.modules():
+        if isinstance(m, torch.nn.Linear):
+            m.weight.data.normal_(0, 1.0 / m.weight.shape[1] ** 0.5)
+            m.bias.data.normal_(0, 0.05)
+    head = head.to(dev)
+    z = torch.randn(rows, 2048, device=dev)
+    for _ in range(3):
+        head.sample(z, 1.0, 1.0, seed=1)
+    ms, _ = _timed_ms(lambda: head.sample(z, 1.0, 1.0, seed=2), 20)
+    head.engine(rows).check()
+    w = dict(head.state_dict())
+    noise, step_noise = torch.randn(rows, 8, device=dev), torch.randn(100, rows, 8, device=dev)
+    D.p_sample_loop(w, z, noise, step_noise)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    D.p_sample_loop(w, z, noise, step_noise)
+    torch.cuda.synchronize()
+    eager_ms = (time.perf_counter() - t0) * 1e3
+    layer_bytes = 4 * (2 * 3 * 1024 * 1024 + 16 * 1024 + 8 * 1024)       # weights one diffusion step touches (shared memory)
+    return {"workload": f"diffusion head: DiffLoss.sample, {rows} row(s), z 2048 -> latent 8, width 1024, depth 3, 100 steps, fp32",
+            "value": round(rows / ms * 1e3, 1), "unit": "latents/s", "ms_per_token": round(ms, 3),
+            "us_per_diffusion_step": round(ms * 10, 2), "grid_barriers_per_step": 7,
+            "bound": "latency: 7 dependent grid-wide exchanges per diffusion step, weights resident in shared memory "
+                     f"({layer_bytes * 100 / 1e6:.0f} MB of weight reads per token never leave the SMs)",
+            "gpu_eager_port": {"ms_per_token": round(eager_ms, 1), "kind": "oracle port on cuda (torch library kernels, fp32)"}}
 
 
 def _conv_flops(module, x_shape):
@@ -588,6 +627,7 @@ def run_vlg(args):
                              ("gpu_eager_baseline", lambda: extra_gpu_eager(dev, args.ref_decode_steps)),
                              ("cfg5_vq", lambda: extra_cfg5(dev)),
                              ("decode_code", lambda: extra_decode_code(dev, pk)),
+                             ("diff_head", lambda: extra_diff_head(dev)),
                              ("cfg3", lambda: extra_cfg3(dev, peak_scale)),
                              ("cfg4_b8", lambda: extra_cfg4(dev, peak_scale, 8))):
                 try:
