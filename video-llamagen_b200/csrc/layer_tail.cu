@@ -47,16 +47,6 @@ constexpr int kLtStagesNarrow = 9;
 constexpr int kLtPairABytes = 64 * 128;
 constexpr int kLtStageBytesPair = kLtPairABytes + 8192;
 constexpr int kLtStagesPair = 13;
-// few-row mode (<= 16 rows, layer_tail_few_kernel): a stage = a 16-row activation tile (2 KB; the MMA still reads 128 rows --
-// the 112 beyond are whatever follows in shared memory and only feed accumulator lanes nobody reads) + a weight tile of up to
-// 64 rows; the normed activations of the w1|w3 and wqkv phases do not come through the ring at all but from a [16 x dim]
-// slab the CTA writes itself (lt_slab_norm)
-constexpr int kLtFewRows = 16;
-constexpr int kLtFewABytes = kLtFewRows * 128;
-constexpr int kLtStageBytesFew = kLtFewABytes + 8192;
-constexpr int kLtStagesFew = 14;
-constexpr int kLtSlabBytes = 24 * kLtFewABytes;      // dim <= 1536
-constexpr int kLtSlabPad = 16384;                       // what the MMA reads past the last 16-row tile
 constexpr int kLtTmemCols = 256;          // two accumulators (one per MMA-issuing warp), 128 columns apart
 constexpr int kLtIssuer2 = 2 + kLtReaders;   // second MMA-issuing warp: the first warp behind the TMEM readers
 constexpr int lt_smem_bytes(int stages, int stage_bytes) { return stages * stage_bytes + 1024 /*align slack*/ + 512 /*barriers*/; }
@@ -223,9 +213,7 @@ __device__ __forceinline__ void lt_pf_slice(const LtParams& P, int slice, int n_
 // (128 + BN) to (64 + BN/2) rows per k-block.  `full` barriers live in the leader and count the bytes of both CTAs.
 template <bool PAIR> __device__ __forceinline__ int lt_unit_id() { return PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x; }
 
-// AR: bytes of a stage in front of the weight tile (the activation tile's slot); P_a_bytes: activation bytes the phase's own
-// loads will add to each stage (0 when its A operand does not come through the ring)
-template <int ST, int SB, bool PAIR, int AR = (PAIR ? kLtPairABytes : kLtABytes)>
+template <int ST, int SB, bool PAIR>
 __device__ __forceinline__ void lt_prefetch_b(const LtGemm& G, const TensorMap* tmB, uint8_t* ring, LtSmem<ST>& sm, uint32_t g, uint32_t P_a_bytes) {
   const LtUnit v = lt_unit(G, lt_unit_id<PAIR>());
   if (!v.valid) return;
@@ -244,21 +232,18 @@ __device__ __forceinline__ void lt_prefetch_b(const LtGemm& G, const TensorMap* 
       const uint32_t s = (g + kb) % ST, it = (g + kb) / ST;
       mbar_wait(&sm.empty[s], (it & 1) ^ 1);
       mbar_expect_tx(&sm.full[s], tx);
-      tma_load_2d_hint(ring + s * SB + AR, tmB, &sm.full[s], (v.kb0 + kb) * 64, v.n0, kEvictFirst);
+      tma_load_2d_hint(ring + s * SB + kLtABytes, tmB, &sm.full[s], (v.kb0 + kb) * 64, v.n0, kEvictFirst);
     }
   }
 }
 
 // MODE: -1 = store the fp32 partial tile (split-K, reduced by the following row phase); EPI_SWIGLU / EPI_QKV_ROPE = the unit
 // owns all of K and applies the elementwise tail straight from TMEM (lane == row).
-// EPI_RESID (few-row mode): the unit owns all of K and folds the tile into the residual stream in place, h <- T(h + T(acc)).
-// ALOC (few-row mode): the A operand is the CTA's own slab (k-block kb at slab + kb * AR), nothing but weights goes through the ring.
-// next_tx_a: activation bytes per stage of the NEXT phase (for the expect_tx armed together with its weight prefetch).
-template <int MODE, int ST, int SB, bool PAIR, int AR = (PAIR ? kLtPairABytes : kLtABytes), bool ALOC = false>
+template <int MODE, int ST, int SB, bool PAIR>
 __device__ __forceinline__ void lt_gemm_phase(const LtGemm& G, const TensorMap* tmA, const TensorMap* tmB,
                                               const LtGemm* Gnext, const TensorMap* tmBnext, const LtParams& P,
                                               const EpiParams& E, uint8_t* ring, LtSmem<ST>& sm, uint32_t tmem_acc, uint32_t& g, uint32_t& acc_uses,
-                                              int ts_slot, uint32_t next_tx_a = 0xffffffffu, const uint8_t* slab = nullptr) {
+                                              int ts_slot) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const LtUnit u = lt_unit(G, lt_unit_id<PAIR>());
   const uint32_t nkb = u.valid ? (uint32_t)u.nkb : 0u;
@@ -283,24 +268,22 @@ __device__ __forceinline__ void lt_gemm_phase(const LtGemm& G, const TensorMap* 
             tma_load_2d_pair(a + kLtPairABytes, tmB, &sm.full[s], (u.kb0 + kb) * 64, u.n0 + (int)rank * (G.BN >> 1), kEvictFirst);
           }
         } else {
-          if constexpr (!ALOC) {
-            for (int kb = 0; kb < pre; ++kb) {
-              const uint32_t s = (g + kb) % ST;
-              tma_load_2d_hint(ring + s * SB, tmA, &sm.full[s], (u.kb0 + kb) * 64, 0, kEvictLast);
-            }
+          for (int kb = 0; kb < pre; ++kb) {
+            const uint32_t s = (g + kb) % ST;
+            tma_load_2d_hint(ring + s * SB, tmA, &sm.full[s], (u.kb0 + kb) * 64, 0, kEvictLast);
           }
-          const uint32_t tx = (ALOC ? 0u : P.a_bytes) + G.BN * 128;
+          const uint32_t tx = P.a_bytes + G.BN * 128;
           for (int kb = pre; kb < u.nkb; ++kb) {
             const uint32_t s = (g + kb) % ST, it = (g + kb) / ST;
             mbar_wait(&sm.empty[s], (it & 1) ^ 1);
             mbar_expect_tx(&sm.full[s], tx);
             uint8_t* a = ring + s * SB;
-            if constexpr (!ALOC) tma_load_2d_hint(a, tmA, &sm.full[s], (u.kb0 + kb) * 64, 0, kEvictLast);
-            tma_load_2d_hint(a + AR, tmB, &sm.full[s], (u.kb0 + kb) * 64, u.n0, kEvictFirst);
+            tma_load_2d_hint(a, tmA, &sm.full[s], (u.kb0 + kb) * 64, 0, kEvictLast);
+            tma_load_2d_hint(a + kLtABytes, tmB, &sm.full[s], (u.kb0 + kb) * 64, u.n0, kEvictFirst);
           }
         }
       }
-      if (Gnext != nullptr) lt_prefetch_b<ST, SB, PAIR, AR>(*Gnext, tmBnext, ring, sm, g + nkb, next_tx_a == 0xffffffffu ? P.a_bytes : next_tx_a);
+      if (Gnext != nullptr) lt_prefetch_b<ST, SB, PAIR>(*Gnext, tmBnext, ring, sm, g + nkb, P.a_bytes);
     }
     __syncwarp();
   } else if (warp == 1 || warp == kLtIssuer2) {
@@ -316,7 +299,7 @@ __device__ __forceinline__ void lt_gemm_phase(const LtGemm& G, const TensorMap* 
         mbar_wait(&sm.full[s], it & 1);
         tc_fence_after();
         const uint32_t a_addr = smem_u32(ring + s * SB);
-        const uint64_t adesc = umma_desc_sw128(ALOC ? smem_u32(slab) + (uint32_t)(u.kb0 + kb) * AR : a_addr), bdesc = umma_desc_sw128(a_addr + AR);
+        const uint64_t adesc = umma_desc_sw128(a_addr), bdesc = umma_desc_sw128(a_addr + (PAIR ? kLtPairABytes : kLtABytes));
         if constexpr (PAIR) {
 #pragma unroll
           for (int k = 0; k < 4; ++k) umma_bf16_pair(acc, adesc + 2 * k, bdesc + 2 * k, idesc, (kb >= 2 || k != 0));
@@ -357,39 +340,10 @@ __device__ __forceinline__ void lt_gemm_phase(const LtGemm& G, const TensorMap* 
           for (int i = 0; i < 8; ++i) rope_cs[i] = tab[i];
         }
       }
-      // EPI_RESID: the residual rows this warp will update, requested while the main loop runs
-      uint4 res_pre[2] = {};
-      if constexpr (MODE == EPI_RESID) {
-        if (r < P.rows && half * 16 < ncol) {
-          const __nv_bfloat16* hp = P.h + (size_t)r * P.dim + u.n0 + cbase + half * 16;
-          res_pre[0] = ldg128_cg(hp);
-          res_pre[1] = ldg128_cg(hp + 8);
-        }
-      }
       mbar_wait(&sm.acc_ready, acc_uses & 1);
       tc_fence_after();
       if (threadIdx.x == 64) LT_TS_AT(ts_slot);
-      if constexpr (MODE == EPI_RESID) {               // gpt.py:257-258: h + wo(..), h + w2(..); G.N == dim
-        for (int c = half * 16; c < ncol; c += 16 * kLtHalves) {
-          float v[16];
-          tmem_ld16(lane_base + c, v);
-          if (two) lt_add_acc16(lane_base + kAcc2 + c, v);
-          if (r < P.rows) {
-            __nv_bfloat16* hp = P.h + (size_t)r * P.dim + u.n0 + cbase + c;
-            const uint4 h0 = c == half * 16 ? res_pre[0] : ldg128_cg(hp), h1 = c == half * 16 ? res_pre[1] : ldg128_cg(hp + 8);
-            const uint32_t hw[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
-            float o[16];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              float a0 = v[2 * i], a1 = v[2 * i + 1];
-              rnd2_bf16(a0, a1);
-              o[2 * i] = __fadd_rn(bf16lo(hw[i]), a0);
-              o[2 * i + 1] = __fadd_rn(bf16hi(hw[i]), a1);
-            }
-            stg256_bf16x16(hp, o);
-          }
-        }
-      } else if constexpr (MODE < 0) {
+      if constexpr (MODE < 0) {
         float* dst = P.part + ((size_t)u.split * P.rows + r) * G.N + u.n0 + cbase;
         for (int c = half * 16; c < ncol; c += 16 * kLtHalves) {
           float v[16];
@@ -627,130 +581,6 @@ layer_tail_kernel(const __grid_constant__ TensorMap tmAttn, const __grid_constan
   }
 }
 
-
-// ---------------------------------------------------------------------------------------------------- few-row mode
-// With <= 16 rows (the t2v loop at batch 1-8, single images, the reference's published 8-image workload) the kernel above is
-// pure latency: its six phases take as long as at 128 rows.  Here the two row phases and the split-K exchange
-// disappear: wo and w2 own all of K (their weight slices are all an SM has to pull: the activation tile is 2 KB per k-block)
-// and fold their tile into the residual stream straight from TMEM; the RMSNorm in front of w1|w3 and wqkv is recomputed by
-// EVERY CTA for all rows (16 x dim values: less than a microsecond) and written as the GEMM's A operand into the CTA's own
-// shared memory, in the 128B-swizzled K-major layout TMA would have produced.  Three grid barriers instead of five, four
-// phases instead of six, no fp32 partials.
-
-// xn <- T(T(h * rsqrt(mean(h^2) + eps)) * w) for all rows, into the slab: k-block kb is a [16 rows x 64] tile at kb * 2 KB,
-// row r at (r / 8) * 1024 + (r % 8) * 128 inside it, its 16-byte chunk j at ((j ^ (r % 8)) * 16).  gpt.py:143-148.
-__device__ __forceinline__ void lt_slab_norm(const LtParams& P, const __nv_bfloat16* w, uint8_t* slab) {
-  if (threadIdx.x < 32) return;                    // the producer warp keeps requesting weight tiles
-  const int wk = (threadIdx.x >> 5) - 1, lane = threadIdx.x & 31;
-  constexpr int kWarps = kLtWorkers / 32, kMaxV = kLtSlabBytes / kLtFewABytes * 8 / 32;      // 16-byte chunks per lane and row
-  const int nvec = P.dim / 8;
-  for (int r = wk; r < P.rows; r += kWarps) {
-    uint4 hv[kMaxV];
-    float ss = 0.f;
-#pragma unroll
-    for (int j = 0; j < kMaxV; ++j) {
-      const int c = lane + 32 * j;
-      if (c < nvec) {
-        hv[j] = ldg128_cg(P.h + (size_t)r * P.dim + c * 8);
-        const uint32_t hw[4] = {hv[j].x, hv[j].y, hv[j].z, hv[j].w};
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float a = bf16lo(hw[i]), b = bf16hi(hw[i]);
-          ss = __fadd_rn(ss, __fmul_rn(a, a));
-          ss = __fadd_rn(ss, __fmul_rn(b, b));
-        }
-      }
-    }
-    ss = warp_sum(ss);
-    const float rs = rsqrtf(__fdiv_rn(ss, (float)P.dim) + P.eps);
-    uint8_t* row = slab + (r >> 3) * 1024 + (r & 7) * 128;
-#pragma unroll
-    for (int j = 0; j < kMaxV; ++j) {
-      const int c = lane + 32 * j;
-      if (c < nvec) {
-        const uint4 gv = __ldg(reinterpret_cast<const uint4*>(w + c * 8));
-        const uint32_t hw[4] = {hv[j].x, hv[j].y, hv[j].z, hv[j].w}, gw[4] = {gv.x, gv.y, gv.z, gv.w};
-        uint32_t o[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          float y0 = __fmul_rn(bf16lo(hw[i]), rs), y1 = __fmul_rn(bf16hi(hw[i]), rs);
-          rnd2_bf16(y0, y1);
-          o[i] = pack_bf16(__fmul_rn(y0, bf16lo(gw[i])), __fmul_rn(y1, bf16hi(gw[i])));
-        }
-        *reinterpret_cast<uint4*>(row + (c >> 3) * kLtFewABytes + (((c & 7) ^ (r & 7)) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
-      }
-    }
-  }
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> the tensor core's reads
-  lt_workers_sync();
-}
-
-template <int ST, int SB>
-__global__ void __launch_bounds__(kLtThreads, 1)
-layer_tail_few_kernel(const __grid_constant__ TensorMap tmAttn, const __grid_constant__ TensorMap tmFfn,
-                      const __grid_constant__ TensorMap tmWo, const __grid_constant__ TensorMap tmW13,
-                      const __grid_constant__ TensorMap tmW2, const __grid_constant__ TensorMap tmWqkv, const LtParams P) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* slab = ring + ST * SB;                      // over-reads of the ring's last activation tile land here
-  LtSmem<ST>& sm = *reinterpret_cast<LtSmem<ST>*>(slab + kLtSlabBytes + kLtSlabPad);
-  const int warp = threadIdx.x >> 5;
-  constexpr int AR = kLtFewABytes;
-
-  if (threadIdx.x == 0) {
-    if (P.has_front) { tma_prefetch_desc(&tmAttn); tma_prefetch_desc(&tmFfn); tma_prefetch_desc(&tmWo); tma_prefetch_desc(&tmW13); tma_prefetch_desc(&tmW2); }
-    if (P.has_qkv) tma_prefetch_desc(&tmWqkv);
-    for (int s = 0; s < ST; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], 1); }
-    mbar_init(&sm.acc_ready, 2);
-    fence_mbar_init();
-  }
-  if (warp == 1) tmem_alloc<kLtTmemCols>(&sm.tmem_slot);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_acc = sm.tmem_slot;
-
-  pdl_launch_dependents();
-  uint32_t g = 0, acc_uses = 0;
-  unsigned bar_target = 0;
-  if (warp == 0) {                                      // the first GEMM's weight tiles do not depend on the previous kernel
-    if (elect_one()) {
-      if (P.has_front) lt_prefetch_b<ST, SB, false, AR>(P.g_wo, &tmWo, ring, sm, 0, P.a_bytes);
-      else if (P.has_qkv) lt_prefetch_b<ST, SB, false, AR>(P.g_qkv, &tmWqkv, ring, sm, 0, 0u);
-    }
-    __syncwarp();
-  }
-  pdl_wait();
-
-  if (P.has_front) {
-    lt_gemm_phase<EPI_RESID, ST, SB, false, AR, false>(P.g_wo, &tmAttn, &tmWo, &P.g_w13, &tmW13, P, P.ffn, ring, sm, tmem_acc, g, acc_uses, 16, 0u);
-    lt_grid_barrier(P.bar, bar_target, P.err);
-    lt_slab_norm(P, P.norm1_w, slab);
-    lt_gemm_phase<EPI_SWIGLU, ST, SB, false, AR, true>(P.g_w13, nullptr, &tmW13, &P.g_w2, &tmW2, P, P.ffn, ring, sm, tmem_acc, g, acc_uses, 18, P.a_bytes, slab);
-    lt_grid_barrier(P.bar, bar_target, P.err);
-    lt_gemm_phase<EPI_RESID, ST, SB, false, AR, false>(P.g_w2, &tmFfn, &tmW2, P.has_qkv ? &P.g_qkv : nullptr, &tmWqkv, P, P.ffn, ring, sm, tmem_acc, g, acc_uses, 20, 0u);
-    lt_grid_barrier(P.bar, bar_target, P.err);
-  }
-  if (P.has_qkv) {
-    lt_slab_norm(P, P.norm2_w, slab);
-    lt_gemm_phase<EPI_QKV_ROPE, ST, SB, false, AR, true>(P.g_qkv, nullptr, &tmWqkv, nullptr, nullptr, P, P.rope, ring, sm, tmem_acc, g, acc_uses, 22, 0u, slab);
-  } else {
-    lt_norm_phase<ST>(nullptr, P.norm2_w, P, sm);        // after the last layer: the head GEMM reads xn from global memory
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    const unsigned old = atomicAdd(P.bar + 1, 1u);
-    if (old == gridDim.x - 1) {
-      P.bar[0] = 0;
-      P.bar[1] = 0;
-      __threadfence();
-    }
-  }
-  if (warp == 1) tmem_dealloc<kLtTmemCols>(tmem_acc);
-}
-
 // ---------------------------------------------------------------------------------------------------- host
 // Tile shape and split count per GEMM: bytes a CTA pulls through its L2 port (activation + weight slices), pushes out
 // (partial tile) and the row phase pulls back, with at most one unit per CTA.
@@ -845,24 +675,6 @@ static bool lt_pair_plan(int rows, int dim, int hidden, int sms, LtGemm* wo, LtG
          lt_pick_pair(dim, hidden, pairs, true, 64, w2) && lt_pick_pair(3 * dim, dim, pairs, false, 64, qkv);
 }
 
-
-// few-row mode: every GEMM owns all of K; the narrowest column tile that still gives every unit its own CTA
-static bool lt_pick_few(int N, int K, int sms, int min_bn, LtGemm* out) {
-  if (K % 64 != 0) return false;
-  for (int bn : {16, 32, 64}) {
-    if (bn < min_bn || N % bn || N / bn > sms) continue;
-    out->N = N; out->K = K; out->BN = bn; out->S = 1; out->n_tiles = N / bn; out->kb_per = K / 64;
-    return true;
-  }
-  return false;
-}
-static bool lt_few_plan(int rows, int dim, int hidden, int sms, LtGemm* wo, LtGemm* w13, LtGemm* w2, LtGemm* qkv) {
-  static const bool off = [] { const char* e = getenv("VLG_LT_FEW"); return e && e[0] == '0'; }();
-  if (off || rows > kLtFewRows || dim / 64 * kLtFewABytes > kLtSlabBytes) return false;
-  return lt_pick_few(dim, dim, sms, 16, wo) && lt_pick_few(2 * hidden, dim, sms, 32, w13) && lt_pick_few(dim, hidden, sms, 16, w2) &&
-         lt_pick_few(3 * dim, dim, sms, 16, qkv);
-}
-
 bool layer_tail_supported(int rows, int dim, int hidden) {
   static const bool off = [] { const char* e = getenv("VLG_LT"); return e && e[0] == '0'; }();
   if (off) return false;
@@ -902,9 +714,8 @@ int launch_layer_tail(const LtLaunch& a, cudaStream_t st) {
   P.rows = a.rows; P.dim = a.dim; P.hidden = a.hidden;
   P.has_front = a.wo != nullptr;
   P.has_qkv = a.wqkv != nullptr;
-  const bool few = lt_few_plan(a.rows, a.dim, a.hidden, sms, &P.g_wo, &P.g_w13, &P.g_w2, &P.g_qkv);
-  const bool pair = !few && lt_pair_plan(a.rows, a.dim, a.hidden, sms, &P.g_wo, &P.g_w13, &P.g_w2, &P.g_qkv);
-  if (!pair && !few) {
+  const bool pair = lt_pair_plan(a.rows, a.dim, a.hidden, sms, &P.g_wo, &P.g_w13, &P.g_w2, &P.g_qkv);
+  if (!pair) {
     lt_pick(a.dim, a.dim, sms, true, &P.g_wo);
     lt_pick(2 * a.hidden, a.dim, sms, false, &P.g_w13);
     lt_pick(a.dim, a.hidden, sms, true, &P.g_w2);
@@ -912,7 +723,7 @@ int launch_layer_tail(const LtLaunch& a, cudaStream_t st) {
   }
   const LtGemm* gs[2] = {&P.g_wo, &P.g_w2};
   for (const LtGemm* g : gs)
-    VLG_REQUIRE(few || (size_t)g->S * a.rows * g->N * sizeof(float) <= a.part_bytes, "layer_tail: scratch too small (%zu bytes)", a.part_bytes);
+    VLG_REQUIRE((size_t)g->S * a.rows * g->N * sizeof(float) <= a.part_bytes, "layer_tail: scratch too small (%zu bytes)", a.part_bytes);
   P.part = a.part;
   P.h = static_cast<__nv_bfloat16*>(a.h);
   P.xn = static_cast<__nv_bfloat16*>(a.xn);
@@ -957,15 +768,6 @@ int launch_layer_tail(const LtLaunch& a, cudaStream_t st) {
   if (P.has_qkv)
     if ((rc = make_tmap_bf16_2d(&tmWqkv, a.wqkv, (uint64_t)3 * a.dim, (uint64_t)a.dim, (uint64_t)a.dim * 2, P.g_qkv.BN >> (pair ? 1 : 0), 64, true))) return rc;
 
-  if (few) {
-    auto kern = layer_tail_few_kernel<kLtStagesFew, kLtStageBytesFew>;
-    const int smem = kLtStagesFew * kLtStageBytesFew + kLtSlabBytes + kLtSlabPad + 1024 + 512;
-    static PerDeviceOnce attr_once_few;
-    VLG_CUDA(attr_once_few([&] { return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); }));
-    VLG_CUDA(launch_kernel(kern, dim3(sms), dim3(kLtThreads), (size_t)smem, st, tmAttn, tmFfn, tmWo, tmW13, tmW2, tmWqkv, P));
-    VLG_LAUNCH_CHECK();
-    return VLG_OK;
-  }
   if (pair) {
     auto kern = layer_tail_kernel<kLtStagesPair, kLtStageBytesPair, true>;
     const int smem = lt_smem_bytes(kLtStagesPair, kLtStageBytesPair);
