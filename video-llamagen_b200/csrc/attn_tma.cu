@@ -20,7 +20,10 @@
 namespace vlg {
 
 constexpr int kTile = 32;                   // cache positions per TMA tile
-constexpr int kCW = 8;                      // consumer warps
+#ifndef VLG_ATTN_CW
+#define VLG_ATTN_CW 8
+#endif
+constexpr int kCW = VLG_ATTN_CW;            // consumer warps
 #ifndef VLG_ATTN_STAGES
 #define VLG_ATTN_STAGES 16
 #endif

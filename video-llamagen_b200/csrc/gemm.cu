@@ -295,9 +295,69 @@ gemm_f32_kernel(const float* __restrict__ x, const float* __restrict__ w, int ro
   }
 }
 
+
+// rows <= 8 (every position of the fp32 decode loop): the same sums in the same order -- the results are bit-identical to
+// gemm_f32_kernel's -- spread over four times as many warps.  The fp32 path streams every weight once per position, so what
+// matters is bytes in flight; with 8 columns per warp a [2048 x 2048] layer leaves 256 warps for the whole chip (measured:
+// 1.6 TB/s over a GPT-1B trunk position).  Here four warps share an 8-column group, two columns each, the group's sums meet
+// in shared memory and one warp runs the 8-column epilogue.
+constexpr int kF32FewWarps = 8;      // two 8-column groups per CTA
+
+template <int EPI>
+__global__ void __launch_bounds__(kF32FewWarps * 32)
+gemm_f32_few_kernel(const float* __restrict__ x, const float* __restrict__ w, int rows, int N, int K, EpiParams P) {
+  __shared__ float sums[2][8][8];      // [group][row][column]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int grp = warp >> 2, sub = warp & 3;
+  const int n0 = (blockIdx.x * 2 + grp) * 8, nc = n0 + sub * 2;
+  pdl_launch_dependents();
+  pdl_wait();
+  const bool live = n0 < N;
+  if (live) {
+    float acc[8][2];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i][0] = acc[i][1] = 0.f;
+    const float* w0 = w + (size_t)nc * K;
+    const float* w1 = w0 + K;
+#pragma unroll 4
+    for (int k = lane * 4; k < K; k += 128) {
+      const float4 a = *reinterpret_cast<const float4*>(w0 + k), b = *reinterpret_cast<const float4*>(w1 + k);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (i >= rows) continue;
+        const float4 xv = *reinterpret_cast<const float4*>(x + (size_t)i * K + k);
+        float s = acc[i][0], t = acc[i][1];
+        s = __fmaf_rn(xv.x, a.x, s); s = __fmaf_rn(xv.y, a.y, s); s = __fmaf_rn(xv.z, a.z, s); s = __fmaf_rn(xv.w, a.w, s);
+        t = __fmaf_rn(xv.x, b.x, t); t = __fmaf_rn(xv.y, b.y, t); t = __fmaf_rn(xv.z, b.z, t); t = __fmaf_rn(xv.w, b.w, t);
+        acc[i][0] = s; acc[i][1] = t;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (i >= rows) continue;
+      const float s = warp_sum(acc[i][0]), t = warp_sum(acc[i][1]);
+      if (lane == 0) { sums[grp][i][sub * 2] = s; sums[grp][i][sub * 2 + 1] = t; }
+    }
+  }
+  __syncthreads();
+  if (live && sub == 0 && lane < rows) {
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = sums[grp][lane][j];
+    epi8<EPI, float>(lane, n0, v, P);
+  }
+}
+
 template <int EPI>
 static int launch_f32(const void* x, const void* w, int rows, int N, int K, const EpiParams& P, cudaStream_t st) {
   int groups = N / 8;
+  static const bool few_off = [] { const char* e = getenv("VLG_F32_FEW"); return e && e[0] == '0'; }();    // A/B
+  if (rows <= 8 && !few_off) {
+    VLG_CUDA(launch_kernel(gemm_f32_few_kernel<EPI>, dim3((groups + 1) / 2), dim3(kF32FewWarps * 32), 0, st,
+                           static_cast<const float*>(x), static_cast<const float*>(w), rows, N, K, P));
+    VLG_LAUNCH_CHECK();
+    return VLG_OK;
+  }
   VLG_CUDA(launch_kernel(gemm_f32_kernel<EPI>, dim3((groups + kF32Warps - 1) / kF32Warps), dim3(kF32Warps * 32), 0, st,
                          static_cast<const float*>(x), static_cast<const float*>(w), rows, N, K, P));
   VLG_LAUNCH_CHECK();
