@@ -330,13 +330,20 @@ def extra_diff_head(dev, rows=1):
     D.p_sample_loop(w, z, noise, step_noise)
     torch.cuda.synchronize()
     eager_ms = (time.perf_counter() - t0) * 1e3
+    # the same call on this host's cores (the reference's own CPU path is this arithmetic in torch): ONE token, bounded
+    cpu_w = {k: v.detach().cpu() for k, v in w.items()}
+    t0 = time.perf_counter()
+    D.p_sample_loop(cpu_w, z.cpu(), noise.cpu(), step_noise.cpu())
+    cpu_ms = (time.perf_counter() - t0) * 1e3
     layer_bytes = 4 * (2 * 3 * 1024 * 1024 + 16 * 1024 + 8 * 1024)       # weights one diffusion step touches (shared memory)
     return {"workload": f"diffusion head: DiffLoss.sample, {rows} row(s), z 2048 -> latent 8, width 1024, depth 3, 100 steps, fp32",
             "value": round(rows / ms * 1e3, 1), "unit": "latents/s", "ms_per_token": round(ms, 3),
             "us_per_diffusion_step": round(ms * 10, 2), "grid_barriers_per_step": 7,
             "bound": "latency: 7 dependent grid-wide exchanges per diffusion step, weights resident in shared memory "
                      f"({layer_bytes * 100 / 1e6:.0f} MB of weight reads per token never leave the SMs)",
-            "gpu_eager_port": {"ms_per_token": round(eager_ms, 1), "kind": "oracle port on cuda (torch library kernels, fp32)"}}
+            "gpu_eager_port": {"ms_per_token": round(eager_ms, 1), "kind": "oracle port on cuda (torch library kernels, fp32)"},
+            "cpu_baseline": {"ms_per_token": round(cpu_ms, 1), "cores": torch.get_num_threads(), "kind": "port",
+                             "sample": "one token (100 sampling steps) on the host cores, fp32"}}
 
 
 def _conv_flops(module, x_shape):

@@ -165,6 +165,14 @@ int vlg_begin(vlg_ctx* ctx, int rows, const uint8_t* prefix_mask_dev, void* stre
 int vlg_forward_pos(vlg_ctx* ctx, const int64_t* tokens_dev, const int64_t* labels_dev, const void* embeds_dev,
                     int pos, float* logits_dev, void* hidden_dev, void* stream);
 
+/* The whole conditioning prefix in one call (t2i / t2v: gpt.py:351-352 at S = cls_token_num positions, the reference's
+ * prefill shape, generate.py:77-86): embeds_dev dtype [rows, T, dim] = the caption projection of every row (vlg_mlp which = 0),
+ * positions 0..T-1, causal attention inside the prefix under the mask given to vlg_begin.  K/V of the prefix land in the
+ * caches; hidden_dev dtype [rows, dim] / logits_dev fp32 [rows, V] receive the LAST position's final-normed hidden state /
+ * logits (either may be NULL) -- the only position the reference's callers use.  Real GEMMs over rows*T rows instead of T
+ * single-position passes. */
+int vlg_forward_prefix(vlg_ctx* ctx, const void* embeds_dev, float* logits_dev, void* hidden_dev, void* stream);
+
 /* Caption / latent projection MLP fc2(gelu_tanh(fc1 x)) (gpt.py:118-131): which = 0 cap_proj,
  * 1 vae_latent_adapter, 2 vae_latent_adapter2.  x_dev dtype [n, in], out_dev dtype [n, out].
  * bf16 only: `in` is rounded up to a multiple of 64 and `out` to a multiple of 16 (tensor-core tile granularity): the

@@ -158,3 +158,30 @@ def test_generate_video_diff_loop_matches_the_reference(golden):
     assert rel_err(seq.cpu(), ref) < 5 * REL, rel_err(seq.cpu(), ref)
     with pytest.raises(NotImplementedError):
         generate(m, torch.from_numpy(g["cond"]).to(DEV), 2, cfg_scale=4.0)
+
+
+def test_forward_prefix_equals_stepped_prefill(golden):
+    """vlg_forward_prefix (all caption positions in one pass) against stepping them one by one through vlg_forward_pos:
+    same hidden state at the last position, same K/V in the caches (checked through the next position's output)."""
+    g = golden("diff_generate.npz")
+    m = VD.Transformer(VD.ModelArgs(dim=128, n_layer=2, n_head=2, block_size=16, cls_token_num=6, caption_dim=32,
+                                    vae_embed_dim=8, num_frames=5, t_downsample_size=4, vocab_size=64, diffloss_w=128,
+                                    diffloss_d=3, multiple_of=64)).eval()
+    m.load_state_dict({k[2:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("w.")}, strict=True)
+    m = m.to(DEV)
+    cond = torch.from_numpy(g["cond"]).to(DEV)
+    masks = torch.from_numpy(g["emb_masks"]).to(DEV)
+    lat = torch.randn(1, 1, 8, device=DEV, generator=torch.Generator(DEV).manual_seed(3))
+    outs = []
+    for batched in (False, True):
+        m.setup_caches(1, 6 + 4, None)
+        m.set_prefix_mask(masks)
+        if batched:
+            eng = m._engine
+            h_last = eng.forward_prefix(eng.mlp(0, cond, 128)[:, :6])[1]
+        else:
+            h_last = m(cond_embed=cond, input_pos=torch.arange(6))[0][:, -1]
+        h_next = m(video_latent=lat, input_pos=torch.tensor([6]))[0][:, -1]
+        outs.append((h_last.clone(), h_next.clone()))
+    for a, b in zip(outs[0], outs[1]):
+        assert torch.allclose(a, b, rtol=1e-4, atol=1e-5), float((a - b).abs().max())

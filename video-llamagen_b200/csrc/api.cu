@@ -549,6 +549,27 @@ extern "C" int vlg_forward_pos(vlg_ctx* c, const int64_t* tokens_dev, const int6
   return VLG_OK;
 }
 
+extern "C" int vlg_forward_prefix(vlg_ctx* c, const void* embeds_dev, float* logits_dev, void* hidden_dev, void* stream) {
+  VLG_REQUIRE(c && c->rows > 0, "vlg_forward_prefix: call vlg_begin first");
+  VLG_REQUIRE(embeds_dev != nullptr, "vlg_forward_prefix: null embeds");
+  const vlg_geometry& g = c->g;
+  const int T = g.cls_token_num;
+  VLG_REQUIRE(g.model_type != VLG_C2I && T > 1, "vlg_forward_prefix: the model has no multi-position prefix (use vlg_forward_pos)");
+  VLG_REQUIRE(T <= c->S_max && T <= c->w.rope_rows, "vlg_forward_prefix: prefix of %d positions exceeds the cache", T);
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = ctx_check(c);
+  if (rc) return rc;
+  VLG_CUDA(cudaMemcpyAsync(c->at<void>(c->L.prefix_emb), embeds_dev, (size_t)c->rows * T * g.dim * esz(g.dtype), cudaMemcpyDeviceToDevice, st));
+  if ((rc = run_trunk_prefix(c, T, st))) return rc;
+  if (hidden_dev)
+    VLG_CUDA(cudaMemcpyAsync(hidden_dev, c->at<void>(c->L.xn), (size_t)c->rows * g.dim * esz(g.dtype), cudaMemcpyDeviceToDevice, st));
+  if (logits_dev) {
+    VLG_REQUIRE(c->w.output && g.vocab_size > 0, "vlg_forward_prefix: model has no output head");
+    if ((rc = run_head(c, logits_dev, false, st))) return rc;
+  }
+  return VLG_OK;
+}
+
 extern "C" int vlg_mlp(vlg_ctx* c, int which, const void* x_dev, void* out_dev, int n, void* stream) {
   VLG_REQUIRE(c && x_dev && out_dev && n > 0, "vlg_mlp: bad arguments");
   const vlg_geometry& g = c->g;

@@ -71,6 +71,7 @@ SIGNATURES = {
     "vlg_ctx_check": (_I, [_P, _P]),
     "vlg_begin": (_I, [_P, _I, _P, _P]),
     "vlg_forward_pos": (_I, [_P, _P, _P, _P, _I, _P, _P, _P]),
+    "vlg_forward_prefix": (_I, [_P, _P, _P, _P, _P]),
     "vlg_mlp": (_I, [_P, _I, _P, _P, _I, _P]),
     "vlg_generate": (_I, [_P, C.POINTER(GenerateParams), _P, _P, _P, _P, _P]),
     "vlg_generate_t2v": (_I, [_P, C.POINTER(GenerateParams), _P, _P, _P, _P, _P]),

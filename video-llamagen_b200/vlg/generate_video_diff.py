@@ -48,8 +48,10 @@ def generate(model, cond, max_new_tokens, emb_masks=None, cfg_scale=1.0, cfg_int
         return head.sample(hidden.float(), temperature, cfg_iter, noise=None if noise is None else noise[j],
                            step_noise=None if step_noise is None else step_noise[j])
 
-    hidden, _ = model(video_latent=None, cond_embed=cond_in, input_pos=torch.arange(0, T))
-    lat = draw(hidden[:, -1], 0)
+    # prefill: the whole caption prefix in one pass (only its last position's hidden state is used, generate_video_diff.py:80)
+    eng = model._engine
+    emb = eng.mlp(0, cond_in, model.config.dim)[:, :T]
+    lat = draw(eng.forward_prefix(emb)[1], 0)
     seq[:, 0] = lat
     for j in range(1, max_new_tokens):
         hidden, _ = model(video_latent=lat.to(dtype).unsqueeze(1), cond_embed=None, input_pos=torch.tensor([T + j - 1]))

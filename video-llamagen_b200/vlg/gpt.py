@@ -251,6 +251,16 @@ class Engine:
                                             L.ptr(logits), L.ptr(hidden), L.stream()))
         return logits, hidden
 
+    def forward_prefix(self, embeds, want_logits=False, want_hidden=True):
+        """All cls_token_num prefix positions at once -> (logits, hidden) of the last one (vlg_forward_prefix)."""
+        R, T = self.rows, self.geo.cls_token_num
+        assert embeds.dtype == self.dtype and embeds.shape == (R, T, self.geo.dim)
+        logits = torch.empty(R, self.geo.vocab_size, dtype=torch.float32, device=self.device) if want_logits else None
+        hidden = torch.empty(R, self.geo.dim, dtype=self.dtype, device=self.device) if want_hidden else None
+        with torch.cuda.device(self.device):
+            L.check(L.lib().vlg_forward_prefix(self.ctx, L.ptr(embeds.contiguous()), L.ptr(logits), L.ptr(hidden), L.stream()))
+        return logits, hidden
+
     def mlp(self, which, x, out_features):
         x2 = x.reshape(-1, x.shape[-1]).contiguous()
         out = torch.empty(x2.shape[0], out_features, dtype=self.dtype, device=self.device)
