@@ -144,34 +144,52 @@ __device__ __forceinline__ float dh_input_proj_one(const DhParams& P, const floa
   return a;
 }
 
-// Parameters of one (row, LayerNorm + modulate) application, fetched ahead of the grid barrier in front of the phase that
-// uses them (they depend on the step and the row, not on what the barrier orders): g, o = LayerNorm affine (1, 0 for the
-// output layer), sc1 = 1 + scale, sh = shift, adaLN biases folded in.
-template <int NCH> struct DhPre { float4 g[NCH], o[NCH], sc1[NCH], sh[NCH]; };
+// Modulation of one (row, LayerNorm) application, fetched ahead of the grid barrier in front of the phase that uses it (it
+// depends on the step and the row, not on what the barrier orders): sc1 = 1 + scale, sh = shift, adaLN biases folded in.
+template <int NCH> struct DhPre { float4 sc1[NCH], sh[NCH]; };
+template <int NCH> struct DhAffine { float4 g[NCH], o[NCH]; };
 
 template <int NCH>
-__device__ __forceinline__ void dh_prefetch(const DhParams& P, const float* ln_w, const float* ln_b, const float* mrow, int sh_off, int sc_off,
-                                            int lane, DhPre<NCH>& pre) {
+__device__ __forceinline__ void dh_prefetch(const DhParams& P, const float* mrow, int sh_off, int sc_off, int lane, DhPre<NCH>& pre) {
 #pragma unroll
   for (int ch = 0; ch < NCH; ++ch) {
     const int k = ch * 128 + lane * 4;
-    pre.g[ch] = ln_w ? __ldg(reinterpret_cast<const float4*>(ln_w + k)) : make_float4(1.f, 1.f, 1.f, 1.f);
-    pre.o[ch] = ln_b ? __ldg(reinterpret_cast<const float4*>(ln_b + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
     const float4 sh = __ldg(reinterpret_cast<const float4*>(mrow + sh_off + k)), shb = __ldg(reinterpret_cast<const float4*>(P.ada_b + sh_off + k));
     const float4 sc = __ldg(reinterpret_cast<const float4*>(mrow + sc_off + k)), scb = __ldg(reinterpret_cast<const float4*>(P.ada_b + sc_off + k));
     pre.sh[ch] = make_float4(sh.x + shb.x, sh.y + shb.y, sh.z + shb.z, sh.w + shb.w);
     pre.sc1[ch] = make_float4(1.0f + (sc.x + scb.x), 1.0f + (sc.y + scb.y), 1.0f + (sc.z + scb.z), 1.0f + (sc.w + scb.w));
   }
 }
+// in_ln's affine parameters (model constants: requested together with the activations, they arrive while the statistics are reduced)
+template <int NCH>
+__device__ __forceinline__ void dh_load_affine(const float* ln_w, const float* ln_b, int lane, DhAffine<NCH>& af) {
+#pragma unroll
+  for (int ch = 0; ch < NCH; ++ch) {
+    const int k = ch * 128 + lane * 4;
+    af.g[ch] = __ldg(reinterpret_cast<const float4*>(ln_w + k));
+    af.o[ch] = __ldg(reinterpret_cast<const float4*>(ln_b + k));
+  }
+}
 // u <- (u * g + o) * (1 + scale) + shift   (in_ln's affine, then modulate(): diffloss.py:55-56, 123)
+template <int NCH>
+__device__ __forceinline__ void dh_apply(const DhAffine<NCH>& af, const DhPre<NCH>& pre, float (&u)[NCH * 4]) {
+#pragma unroll
+  for (int ch = 0; ch < NCH; ++ch) {
+    u[ch * 4 + 0] = fmaf(fmaf(u[ch * 4 + 0], af.g[ch].x, af.o[ch].x), pre.sc1[ch].x, pre.sh[ch].x);
+    u[ch * 4 + 1] = fmaf(fmaf(u[ch * 4 + 1], af.g[ch].y, af.o[ch].y), pre.sc1[ch].y, pre.sh[ch].y);
+    u[ch * 4 + 2] = fmaf(fmaf(u[ch * 4 + 2], af.g[ch].z, af.o[ch].z), pre.sc1[ch].z, pre.sh[ch].z);
+    u[ch * 4 + 3] = fmaf(fmaf(u[ch * 4 + 3], af.g[ch].w, af.o[ch].w), pre.sc1[ch].w, pre.sh[ch].w);
+  }
+}
+// the output layer's LayerNorm has no affine parameters (diffloss.py:137)
 template <int NCH>
 __device__ __forceinline__ void dh_apply(const DhPre<NCH>& pre, float (&u)[NCH * 4]) {
 #pragma unroll
   for (int ch = 0; ch < NCH; ++ch) {
-    u[ch * 4 + 0] = fmaf(fmaf(u[ch * 4 + 0], pre.g[ch].x, pre.o[ch].x), pre.sc1[ch].x, pre.sh[ch].x);
-    u[ch * 4 + 1] = fmaf(fmaf(u[ch * 4 + 1], pre.g[ch].y, pre.o[ch].y), pre.sc1[ch].y, pre.sh[ch].y);
-    u[ch * 4 + 2] = fmaf(fmaf(u[ch * 4 + 2], pre.g[ch].z, pre.o[ch].z), pre.sc1[ch].z, pre.sh[ch].z);
-    u[ch * 4 + 3] = fmaf(fmaf(u[ch * 4 + 3], pre.g[ch].w, pre.o[ch].w), pre.sc1[ch].w, pre.sh[ch].w);
+    u[ch * 4 + 0] = fmaf(u[ch * 4 + 0], pre.sc1[ch].x, pre.sh[ch].x);
+    u[ch * 4 + 1] = fmaf(u[ch * 4 + 1], pre.sc1[ch].y, pre.sh[ch].y);
+    u[ch * 4 + 2] = fmaf(u[ch * 4 + 2], pre.sc1[ch].z, pre.sh[ch].z);
+    u[ch * 4 + 3] = fmaf(u[ch * 4 + 3], pre.sc1[ch].w, pre.sh[ch].w);
   }
 }
 
@@ -265,7 +283,7 @@ __global__ void __launch_bounds__(kDhThreads, 1) dh_sample_kernel(const __grid_c
   const int r_first = col_cta ? warp / sp.groups : warp;
   const bool has_first = col_cta ? (warp < sp.items && (warp - r_first * sp.groups) * sp.gcols < P.cpc) : warp < R;
   auto prefetch_block = [&](int b, const float* ms) {
-    if (col_cta && has_first) dh_prefetch<NCH>(P, P.blk[b].ln_w, P.blk[b].ln_b, ms + (size_t)r_first * P.n_mod, b * 3 * W, b * 3 * W + W, lane, pre);
+    if (col_cta && has_first) dh_prefetch<NCH>(P, ms + (size_t)r_first * P.n_mod, b * 3 * W, b * 3 * W + W, lane, pre);
   };
   prefetch_block(0, P.mod + (size_t)(P.steps - 1) * R * P.n_mod);
   unsigned bar_target = 0;
@@ -281,9 +299,11 @@ __global__ void __launch_bounds__(kDhThreads, 1) dh_sample_kernel(const __grid_c
           float u[NCH * 4];
           if (b == 0) dh_input_proj<NCH>(P, xs + (r % half) * C, WiT, lane, u);
           else dh_load_row_cg<NCH>(P.hbuf + (size_t)r * W, lane, u);
+          DhAffine<NCH> af;
+          dh_load_affine<NCH>(P.blk[b].ln_w, P.blk[b].ln_b, lane, af);
+          if (it != warp) dh_prefetch<NCH>(P, mstep + (size_t)r * P.n_mod, b * 3 * W, b * 3 * W + W, lane, pre);
           dh_normalise<NCH>(u, W);
-          if (it != warp) dh_prefetch<NCH>(P, P.blk[b].ln_w, P.blk[b].ln_b, mstep + (size_t)r * P.n_mod, b * 3 * W, b * 3 * W + W, lane, pre);
-          dh_apply<NCH>(pre, u);
+          dh_apply<NCH>(af, pre, u);
           for (int q = q0; q < q1; q += 4) {
             const int nc = min(4, q1 - q), n = blockIdx.x * P.cpc + q + lane;        // lanes [0, nc) finalise one column each
             const float bias = lane < nc ? __ldg(P.blk[b].b1 + n) : 0.f;
@@ -317,7 +337,7 @@ __global__ void __launch_bounds__(kDhThreads, 1) dh_sample_kernel(const __grid_c
         }
       }
       if (b + 1 < P.depth) prefetch_block(b + 1, mstep);
-      else if (!col_cta && has_first) dh_prefetch<NCH>(P, nullptr, nullptr, mstep + (size_t)r_first * P.n_mod, P.depth * 3 * W, P.depth * 3 * W + W, lane, pre);
+      else if (!col_cta && has_first) dh_prefetch<NCH>(P, mstep + (size_t)r_first * P.n_mod, P.depth * 3 * W, P.depth * 3 * W + W, lane, pre);
       dh_grid_barrier(P.bar, bar_target, P.err);
     }
     // ---------------- output layer: out = modulate(LN(h)) . final_w^T + final_b, one column per CTA   (diffloss.py:143-149)
@@ -327,7 +347,7 @@ __global__ void __launch_bounds__(kDhThreads, 1) dh_sample_kernel(const __grid_c
         float u[NCH * 4];
         dh_load_row_cg<NCH>(P.hbuf + (size_t)r * W, lane, u);
         dh_normalise<NCH>(u, W);
-        if (r != warp) dh_prefetch<NCH>(P, nullptr, nullptr, mstep + (size_t)r * P.n_mod, P.depth * 3 * W, P.depth * 3 * W + W, lane, pre);
+        if (r != warp) dh_prefetch<NCH>(P, mstep + (size_t)r * P.n_mod, P.depth * 3 * W, P.depth * 3 * W + W, lane, pre);
         dh_apply<NCH>(pre, u);
         float a = 0.f;
 #pragma unroll
