@@ -9,6 +9,7 @@
 #   prof    ncu evidence: launch list, full captures of the step kernels and the VQ score kernel
 #   pair    cfg-2 with and without CTA pairs in the layer tail (same box), phase timeline
 #   switches  decode parity tests under every A/B switch
+#   diff    diffusion-head sampler: tests, timing per row count, whole generate_video_diff loop, launch list, full ncu capture
 set -u
 mkdir -p gpurun_out
 for what in "$@"; do
@@ -49,6 +50,16 @@ switches)
   for sw in VLG_LT=0 VLG_LT_PAIR=0 VLG_ATTN=generic VLG_PDL=0 VLG_STEPPED_PREFILL=1 VLG_NO_GRAPH=1 VLG_FUSED_NORM=1; do
     env $sw timeout 600 python -m pytest tests/test_gpu_decode.py -q -x 2>&1 | tail -1 | cut -c1-120 | sed "s/^/$sw: /"
   done ;;
+diff)
+  timeout 420 python -m pytest tests/test_gpu_diffusion.py -q 2>&1 | tail -2 | cut -c1-200
+  timeout 200 python tools/diff_bench.py 1 2 4 8 16 2>&1 | tail -5 | tee gpurun_out/diff_bench.txt
+  timeout 300 python tools/diff_generate_bench.py 2>&1 | tail -1 | tee gpurun_out/diff_generate_bench.txt
+  export DIFF_BENCH_ITERS=1 DIFF_BENCH_WARM=1 DIFF_BENCH_NO_EAGER=1
+  python tools/diff_bench.py 1 8 > /dev/null 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/diff_head_launches.csv python tools/diff_bench.py 1 8 > gpurun_out/diff_ncu1.log 2>&1
+  echo "launch list rc=$?"
+  ncu --set full --clock-control none --import-source on -k regex:dh_sample -c 1 -f -o gpurun_out/diff_head_r1 python tools/diff_bench.py 1 > gpurun_out/diff_ncu2.log 2>&1
+  echo "full capture rc=$?"
+  unset DIFF_BENCH_ITERS DIFF_BENCH_WARM DIFF_BENCH_NO_EAGER ;;
 *) echo "unknown recipe $what" ;;
 esac
 done
