@@ -20,7 +20,7 @@ m = GPT_models["GPT-1B"](block_size=1024, cls_token_num=120, caption_dim=2048, v
                          model_type="t2v").eval().to("cuda")
 cond = torch.randn(1, 120, 2048, device="cuda")
 mask = torch.ones(1, 120, device="cuda")
-generate(m, cond, 4, emb_masks=mask, temperature=1.0, cfg_iter=1.0)
+generate(m, cond, 4 + n_tok, emb_masks=mask, temperature=1.0, cfg_iter=1.0)     # sizes the engine (KV cache, weight views) once
 torch.cuda.synchronize()
 t0 = time.perf_counter()
 generate(m, cond, 4, emb_masks=mask, temperature=1.0, cfg_iter=1.0)
