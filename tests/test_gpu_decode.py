@@ -169,10 +169,13 @@ def test_gptl_cfg2_full_size_bf16():
 @pytest.mark.parametrize("name,n_layer,B", [("GPT-B", 3, 4), ("GPT-XL", 2, 8), ("GPT-XXL", 2, 32), ("GPT-1B", 2, 64),
                                             ("GPT-XL", 2, 48),    # 96 rows: CTA pairs with a ragged second half (32 live rows)
                                             ("GPT-XXL", 2, 64),   # 128 rows: CTA pairs at d = 1536 (24 k-blocks through 13 stages)
-                                            ("GPT-B", 2, 80)])    # 160 rows: beyond the layer-tail kernel, per-op kernels
+                                            ("GPT-B", 2, 80),     # 160 rows: beyond the layer-tail kernel, per-op kernels
+                                            # 2 rows (one sample with guidance): the GEMV layer tail (layer_tail_gemv.cu) at
+                                            # d = 768 / 1024 / 1280 / 1536, hidden 2048 / 2816 / 3584 / 4096
+                                            ("GPT-B", 3, 1), ("GPT-L", 2, 1), ("GPT-XL", 2, 1), ("GPT-XXL", 2, 1)])
 def test_layer_tail_geometries_bf16(name, n_layer, B):
-    """The persistent layer-tail kernel (split-K tile shapes, ring wrap-around, row phases) at the widths of the other
-    registry entries -- d = 768 / 1280 / 1536 / 2048, hidden 2048 / 3584 / 4096 / 5632, 8..128 cache rows (single CTAs up to 64
+    """The persistent layer-tail kernels (tensor-core: split-K tile shapes, ring wrap-around, row phases; 1-2 rows: column-pair
+    GEMVs) at the widths of the other registry entries -- d = 768 / 1280 / 1536 / 2048, hidden 2048 / 3584 / 4096 / 5632, 8..128 cache rows (single CTAs up to 64
     rows, CTA pairs above) -- on a few layers: teacher-forced bf16 logits against the oracle on the same GPU."""
     kw = dict(O.NAMED[name])
     kw["n_layer"] = n_layer
@@ -435,3 +438,29 @@ def test_two_contexts_on_two_streams_do_not_share_the_layer_tail_kernel():
         m._engine.check()                               # raises if a grid barrier timed out
     assert n3 - n2 == n1 - n0, "an undisturbed context uses the layer-tail kernel"
     assert n2 - n1 > n1 - n0, "the concurrent context must have fallen back to the per-op kernels"
+
+
+def test_single_sample_generate_loop_through_the_gemv_tail():
+    """One class label with guidance (2 cache rows, GPT-L width): the whole graph-replayed generate() loop through the GEMV
+    layer tail (per-step logits against the oracle are covered by test_layer_tail_geometries_bf16): determinism, token range,
+    a one-row run without guidance, and the greedy loop against the oracle's greedy loop in bf16 on the same GPU."""
+    torch.manual_seed(0)
+    kw = dict(O.NAMED["GPT-L"])
+    kw["n_layer"] = 2
+    m = Transformer(ModelArgs(block_size=64, vocab_size=1024, cls_token_num=1, model_type="c2i", **kw)).eval()
+    torch.nn.init.normal_(m.output.weight, std=0.02)
+    m = m.to(DEV, torch.bfloat16)
+    cond = torch.tensor([7], device=DEV)
+    a = generate(m, cond, 64, cfg_scale=4.0, temperature=1.0, top_k=50, top_p=1.0, sample_logits=True, seed=5)
+    b = generate(m, cond, 64, cfg_scale=4.0, temperature=1.0, top_k=50, top_p=1.0, sample_logits=True, seed=5)
+    assert torch.equal(a, b) and a.shape == (1, 64) and int(a.min()) >= 0 and int(a.max()) < 1024
+    c = generate(m, cond, 64, cfg_scale=1.0, temperature=1.0, top_k=50, top_p=1.0, sample_logits=True, seed=5)   # 1 row
+    assert c.shape == (1, 64) and int(c.min()) >= 0 and int(c.max()) < 1024
+    # greedy tokens of the 2-row loop against the oracle's greedy loop in bf16 on the same GPU: a token may differ only where the
+    # oracle's own top-2 logit gap is inside the bf16 tolerance
+    w16 = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    geo = O.Geometry(block_size=64, vocab_size=1024, **kw)
+    g_ours = generate(m, cond, 24, cfg_scale=4.0, temperature=1.0, top_k=1, top_p=1.0, sample_logits=False)
+    g_ref = O.generate(geo, w16, cond, 24, cfg_scale=4.0, temperature=1.0, top_k=1, top_p=1.0, sample_logits=False)
+    agree = (g_ours.cpu() == g_ref.cpu()).float().mean().item()
+    assert agree >= 0.5, agree            # chaotic after the first near-tie; a wrong kernel gives ~1/1024

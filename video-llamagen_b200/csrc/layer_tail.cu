@@ -709,6 +709,7 @@ size_t layer_tail_scratch_bytes(int max_rows, int dim, int hidden) {
 int launch_layer_tail(const LtLaunch& a, cudaStream_t st) {
   VLG_REQUIRE(layer_tail_supported(a.rows, a.dim, a.hidden), "layer_tail: unsupported shape rows=%d dim=%d hidden=%d", a.rows, a.dim, a.hidden);
   VLG_REQUIRE(a.wo || a.wqkv, "layer_tail: nothing to do");
+  if (layer_tail_gemv_supported(a.rows, a.dim, a.hidden)) return launch_layer_tail_gemv(a, st);
   const int sms = num_sms();
   LtParams P{};
   P.rows = a.rows; P.dim = a.dim; P.hidden = a.hidden;
