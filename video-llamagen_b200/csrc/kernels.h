@@ -75,6 +75,7 @@ int launch_layer_tail(const LtLaunch& a, cudaStream_t st);
 // launch_layer_tail dispatches to it
 bool layer_tail_gemv_supported(int rows, int dim, int hidden);
 int launch_layer_tail_gemv(const LtLaunch& a, cudaStream_t st);
+int layer_tail_gemv_timestamps(unsigned long long* out_host);   // [160][32] globaltimer stamps, VLG_LT_DEBUG=1
 
 // Fused CFG mix + temperature + top-k/top-p + softmax + pick.
 struct SampleArgs {

@@ -796,3 +796,5 @@ extern "C" int vlg_debug_lt_timestamps(unsigned long long* out_host) {
   VLG_CUDA(cudaMemcpyFromSymbol(out_host, vlg::g_lt_ts, sizeof(unsigned long long) * 160 * 32));
   return VLG_OK;
 }
+// the same for the 1-2 row GEMV tail (layer_tail_gemv.cu)
+extern "C" int vlg_debug_gv_timestamps(unsigned long long* out_host) { return vlg::layer_tail_gemv_timestamps(out_host); }

@@ -3,10 +3,14 @@
 //
 // At that size the tensor-core kernel is pure latency -- its six phases, five grid barriers and split-K exchanges take 25 us
 // whatever the row count, for 6 us worth of weights -- and a matrix-vector product needs no tensor core.  Here a warp owns PAIRS
-// of output columns (a RoPE pair, a (w1 x, w3 x) pair) and streams their weight rows straight from global memory into
-// registers (16-byte loads, the next pair's rows in flight while this pair is multiplied), against activation rows it keeps
-// packed in registers; every GEMV owns all of K, so there are no partials and no row phases: the RMSNorm in front of w1|w3 and
-// wqkv is recomputed by every warp (2 rows x dim values) on the way in.  Three grid barriers instead of five:
+// of output columns (a RoPE pair, a (w1 x, w3 x) pair); every CTA owns a contiguous block of pairs of each matrix, and a
+// producer thread streams those weight rows through a 12-stage, 192 KB shared-memory ring with bulk copies
+// (cp.async.bulk, one per stage of up to 16 KB) that runs ahead ACROSS the phases -- weights depend on nothing, so while the
+// grid sits in a barrier the next phase's rows are already landing (a first version loaded each pair's rows from global
+// memory into registers one pair ahead: every pair cost a dependent HBM round trip, 714 against 700 latents/s at cfg-4 B = 1).
+// Consumer warp w takes every 8th stage and multiplies it against activation rows it keeps packed in registers; every GEMV
+// owns all of K, so there are no partials and no row phases: the RMSNorm in front of w1|w3 and wqkv is recomputed by every
+// warp (2 rows x dim values) on the way in.  Three grid barriers instead of five:
 //
 //   wo + residual | B | RMSNorm -> w1|w3 -> SwiGLU | B | w2 + residual | B | RMSNorm -> wqkv -> RoPE + q / KV-cache write
 //
@@ -16,15 +20,17 @@
 
 namespace vlg {
 
-constexpr int kGvThreads = 256;
-constexpr int kGvWarps = kGvThreads / 32;
+constexpr int kGvWarps = 8;                          // consumer warps; warp kGvWarps is the bulk-copy producer
+constexpr int kGvThreads = (kGvWarps + 1) * 32;
+constexpr int kGvStageBytes = 16384;                 // one stage: as many whole column pairs (2 rows of K bf16) as fit, at least one
+constexpr int kGvStages = 12;
+constexpr int kGvActBytes = 16384;                   // the SwiGLU output of all rows, staged once per CTA for the w2 phase (2 x hidden <= 4096 bf16)
 constexpr int kGvMaxRows = 2;
-// ND (template parameter of the kernel) = dim / 256: 256-element chunks per lane and row held in registers at a time -- K = dim in
-// one go, K = hidden (w2) in segments of that many chunks.  Exact-size arrays: with a common maximum the compiler has to
-// keep registers for chunks a model does not have (1.2 KB of spills at 2 rows).
+
 
 struct GvParams {
   int rows, dim, hidden, has_front, has_qkv;
+  int dbg;                   // VLG_LT_DEBUG=1: globaltimer stamps of every CTA's warp 0 (tools/lt_phases.py)
   const __nv_bfloat16 *attn, *wo, *w13, *w2, *wqkv, *norm1_w, *norm2_w;
   __nv_bfloat16 *h, *xn, *ffn;
   float eps;
@@ -33,9 +39,20 @@ struct GvParams {
   volatile unsigned* err;
 };
 
+// phase timestamps (ns) of the last full launch, [160 CTAs][32 slots], read back through vlg_debug_lt_timestamps
+__device__ unsigned long long g_gv_ts[160 * 32];
+#define GV_TS(i)                                                                                      \
+  do {                                                                                                \
+    if (P.dbg && P.has_front && P.has_qkv && threadIdx.x == 0 && blockIdx.x < 160) {                  \
+      unsigned long long t_;                                                                          \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                                          \
+      g_gv_ts[blockIdx.x * 32 + (i)] = t_;                                                            \
+    }                                                                                                 \
+  } while (0)
+
 __device__ __forceinline__ void gv_grid_barrier(unsigned* ctr, unsigned& target, volatile unsigned* err) {
   target += gridDim.x;
-  __syncthreads();
+  asm volatile("bar.sync 1, %0;" ::"n"(kGvWarps * 32) : "memory");      // the consumer warps (the producer never stops for the grid)
   if (threadIdx.x == 0) {
     asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
     unsigned seen, spins = 0;
@@ -55,96 +72,78 @@ __device__ __forceinline__ void gv_grid_barrier(unsigned* ctr, unsigned& target,
       }
     }
   }
-  __syncthreads();
+  asm volatile("bar.sync 1, %0;" ::"n"(kGvWarps * 32) : "memory");
 }
+
+__device__ __forceinline__ void gv_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ uint4 gv_lds128(const void* p) {
+  uint4 r;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(smem_u32(p)));
+  return r;
+}
+struct GvSmem { uint64_t full[kGvStages], empty[kGvStages]; };
+// this CTA's contiguous block of the `pairs` column pairs of a matrix (balanced to within one pair)
+__device__ __forceinline__ void gv_range(int pairs, int& p0, int& p1) {
+  const int base = pairs / (int)gridDim.x, rem = pairs % (int)gridDim.x, c = blockIdx.x;
+  p0 = c * base + min(c, rem);
+  p1 = p0 + base + (c < rem ? 1 : 0);
+}
+__device__ __forceinline__ int gv_pairs_per_stage(int K) { const int n = kGvStageBytes / (4 * K); return n < 1 ? 1 : n; }
 
 __device__ __forceinline__ void gv_unpack(const uint4& v, float (&f)[8]) {
   f[0] = bf16lo(v.x); f[1] = bf16hi(v.x); f[2] = bf16lo(v.y); f[3] = bf16hi(v.y);
   f[4] = bf16lo(v.z); f[5] = bf16hi(v.z); f[6] = bf16lo(v.w); f[7] = bf16hi(v.w);
 }
 
-// this lane's share of R activation rows of length K (K % 256 == 0): chunk ch = elements [(ch * 32 + lane) * 8, + 8), packed bf16
-// (chunks [c0, c0 + MAXCH) of the row)
-template <int R, int MAXCH>
-__device__ __forceinline__ void gv_load_rows(const __nv_bfloat16* base, int K, int rows, int lane, uint4 (&a)[R][MAXCH], int c0 = 0) {
-  const int nch = K >> 8;
-#pragma unroll
-  for (int r = 0; r < R; ++r)
-#pragma unroll
-    for (int ch = 0; ch < MAXCH; ++ch)
-      if (c0 + ch < nch) a[r][ch] = ldg128_cg(base + (size_t)min(r, rows - 1) * K + ((c0 + ch) * 32 + lane) * 8);
-}
-
-// RMSNorm of the rows held in `a` (K = dim), in place: T(T(h * rsqrt(mean(h^2) + eps)) * w)   (gpt.py:143-148)
-template <int R, int ND>
-__device__ __forceinline__ void gv_norm_rows(const __nv_bfloat16* w, int dim, float eps, int lane, uint4 (&a)[R][ND]) {
-  constexpr int nch = ND;
-#pragma unroll
-  for (int r = 0; r < R; ++r) {
-    float ss = 0.f;
-#pragma unroll
-    for (int ch = 0; ch < ND; ++ch)
-      if (ch < nch) {
-        float f[8];
-        gv_unpack(a[r][ch], f);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) ss = __fadd_rn(ss, __fmul_rn(f[i], f[i]));
-      }
-    ss = warp_sum(ss);
-    const float rs = rsqrtf(__fdiv_rn(ss, (float)dim) + eps);
-#pragma unroll
-    for (int ch = 0; ch < ND; ++ch)
-      if (ch < nch) {
-        float f[8], g[8];
-        gv_unpack(a[r][ch], f);
-        gv_unpack(__ldg(reinterpret_cast<const uint4*>(w + (ch * 32 + lane) * 8)), g);
-        uint32_t o[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          float y0 = __fmul_rn(f[2 * i], rs), y1 = __fmul_rn(f[2 * i + 1], rs);
-          rnd2_bf16(y0, y1);
-          o[i] = pack_bf16(__fmul_rn(y0, g[2 * i]), __fmul_rn(y1, g[2 * i + 1]));
-        }
-        a[r][ch] = make_uint4(o[0], o[1], o[2], o[3]);
-      }
+// The activation rows of a phase, ONCE per CTA into shared memory (all consumer threads, one L2 round trip).  When every warp
+// of the grid fetched the rows itself, 1184 warps asked the same 40 cache lines for the same bytes at the same moment.
+// Row r lies at acts + r * 2 K bytes; with `norm_w` the rows are RMS-normalised in place by warps 0 .. rows-1 before anybody
+// reads them: T(T(h * rsqrt(mean(h^2) + eps)) * w)   (gpt.py:143-148).
+// Loops over K are ROLLED on purpose, here and in gv_phase: every phase runs once per launch, so its instructions are fetched
+// cold -- the fully unrolled first version of this kernel was 155 KB of SASS and took 6 us longer with 2 rows than with 1.
+template <int R>
+__device__ __forceinline__ void gv_stage_rows(const __nv_bfloat16* src, int K, int rows, const __nv_bfloat16* norm_w, float eps, uint8_t* acts,
+                                              int warp, int lane) {
+  const int per_row = K >> 3;
+  for (int i = threadIdx.x; i < R * per_row; i += kGvWarps * 32) {
+    const int r = i / per_row, c = i - r * per_row;
+    *reinterpret_cast<uint4*>(acts + (size_t)i * 16) = ldg128_cg(src + (size_t)min(r, rows - 1) * K + c * 8);
   }
-}
-
-// the weight rows of one column pair, this lane's chunks
-template <int MAXCH> struct GvPair { uint4 w[2][MAXCH]; };
-
-template <int MAXCH>
-__device__ __forceinline__ void gv_load_pair(const __nv_bfloat16* W, int K, int n, int lane, GvPair<MAXCH>& p, int c0 = 0) {
-  const int nch = K >> 8;
+  asm volatile("bar.sync 1, %0;" ::"n"(kGvWarps * 32) : "memory");
+  if (norm_w == nullptr) return;
+  if (warp < R) {
+    uint8_t* row = acts + (size_t)warp * 2 * K;
+    float ss = 0.f;
+#pragma unroll 1
+    for (int c = lane; c < per_row; c += 32) {
+      float f[8];
+      gv_unpack(gv_lds128(row + c * 16), f);
 #pragma unroll
-  for (int c = 0; c < 2; ++c)
-#pragma unroll
-    for (int ch = 0; ch < MAXCH; ++ch)
-      if (c0 + ch < nch) p.w[c][ch] = ldg_stream(W + (size_t)(n + c) * K + ((c0 + ch) * 32 + lane) * 8);
-}
-
-// acc[r][c] += sum over this lane's elements of chunks [c0, c0 + MAXCH) of a[r][k] * W[n + c][k]   (fp32, one chain per (row, column))
-template <int R, int MAXCH>
-__device__ __forceinline__ void gv_dot_accum(const GvPair<MAXCH>& p, const uint4 (&a)[R][MAXCH], int K, float (&acc)[R][2], int c0 = 0) {
-  const int nch = K >> 8;
-#pragma unroll
-  for (int ch = 0; ch < MAXCH; ++ch)
-    if (c0 + ch < nch) {
-      float w0[8], w1[8];
-      gv_unpack(p.w[0][ch], w0);
-      gv_unpack(p.w[1][ch], w1);
-#pragma unroll
-      for (int r = 0; r < R; ++r) {
-        float f[8];
-        gv_unpack(a[r][ch], f);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          acc[r][0] = fmaf(f[i], w0[i], acc[r][0]);
-          acc[r][1] = fmaf(f[i], w1[i], acc[r][1]);
-        }
-      }
+      for (int i = 0; i < 8; ++i) ss = __fadd_rn(ss, __fmul_rn(f[i], f[i]));
     }
+    ss = warp_sum(ss);
+    const float rs = rsqrtf(__fdiv_rn(ss, (float)K) + eps);
+#pragma unroll 1
+    for (int c = lane; c < per_row; c += 32) {
+      float f[8], g[8];
+      gv_unpack(gv_lds128(row + c * 16), f);
+      gv_unpack(__ldg(reinterpret_cast<const uint4*>(norm_w + c * 8)), g);
+      uint32_t o[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float y0 = __fmul_rn(f[2 * i], rs), y1 = __fmul_rn(f[2 * i + 1], rs);
+        rnd2_bf16(y0, y1);
+        o[i] = pack_bf16(__fmul_rn(y0, g[2 * i]), __fmul_rn(y1, g[2 * i + 1]));
+      }
+      *reinterpret_cast<uint4*>(row + c * 16) = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+  }
+  asm volatile("bar.sync 1, %0;" ::"n"(kGvWarps * 32) : "memory");
 }
+
 template <int R>
 __device__ __forceinline__ void gv_reduce(float (&acc)[R][2]) {
 #pragma unroll
@@ -156,9 +155,26 @@ __device__ __forceinline__ void gv_reduce(float (&acc)[R][2]) {
 
 enum { GV_RESID = 0, GV_SWIGLU = 1, GV_ROPE = 2 };
 
+// what lane r needs from global memory to finalise row r of the pair (n, n + 1): requested BEFORE the dot product, so the
+// round trip overlaps it (a RoPE finish is two dependent loads -- position, then table entry -- a residual finish one)
+struct GvPre { uint32_t hv; float2 cs; };
+template <int MODE>
+__device__ __forceinline__ GvPre gv_prefetch(const GvParams& P, int n, int pos, int lane) {
+  GvPre pre{0u, make_float2(1.f, 0.f)};
+  if (lane >= P.rows) return pre;
+  if constexpr (MODE == GV_RESID) {
+    asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(pre.hv) : "l"(P.h + (size_t)lane * P.dim + n));
+  } else if constexpr (MODE == GV_ROPE) {
+    const EpiParams& E = P.rope;
+    const int sec = n / E.dim, cc = n - sec * E.dim, dd = cc % E.D;
+    if (sec < 2) pre.cs = __ldg(reinterpret_cast<const float2*>(E.rope) + (size_t)pos * (E.D >> 1) + (dd >> 1));
+  }
+  return pre;
+}
+
 // lane r finalises row r of the pair (n, n + 1)
 template <int MODE, int R>
-__device__ __forceinline__ void gv_finish(const GvParams& P, int n, const float (&acc)[R][2], int lane) {
+__device__ __forceinline__ void gv_finish(const GvParams& P, int n, int pos, const GvPre& pre, const float (&acc)[R][2], int lane) {
   float a0 = acc[0][0], a1 = acc[0][1];
 #pragma unroll
   for (int r = 1; r < R; ++r) {
@@ -169,23 +185,18 @@ __device__ __forceinline__ void gv_finish(const GvParams& P, int n, const float 
   const int r = lane;
   rnd2_bf16(a0, a1);                                   // the nn.Linear result as a bf16 tensor
   if constexpr (MODE == GV_RESID) {                    // gpt.py:257-258
-    uint32_t* hp = reinterpret_cast<uint32_t*>(P.h + (size_t)r * P.dim + n);
-    uint32_t hv;
-    asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(hv) : "l"(hp));
-    const uint32_t o = pack_bf16(__fadd_rn(bf16lo(hv), a0), __fadd_rn(bf16hi(hv), a1));
-    asm volatile("st.global.cg.u32 [%0], %1;" ::"l"(hp), "r"(o) : "memory");
+    const uint32_t o = pack_bf16(__fadd_rn(bf16lo(pre.hv), a0), __fadd_rn(bf16hi(pre.hv), a1));
+    asm volatile("st.global.cg.u32 [%0], %1;" ::"l"(P.h + (size_t)r * P.dim + n), "r"(o) : "memory");
   } else if constexpr (MODE == GV_SWIGLU) {            // gpt.py:167, w1 / w3 rows interleaved
     const float s = rnd<__nv_bfloat16>(silu_f(a0));
     P.ffn[(size_t)r * P.hidden + (n >> 1)] = __float2bfloat16_rn(__fmul_rn(s, a1));
   } else {                                             // gpt.py:215-227, 423-433, 177-185
     const EpiParams& E = P.rope;
-    const int pos = E.pos_ptr ? *E.pos_ptr : E.pos_imm;
     const int sec = n / E.dim, cc = n - sec * E.dim, head = cc / E.D, dd = cc - head * E.D;
     float o0 = a0, o1 = a1;
     if (sec < 2) {
-      const float2 cs = reinterpret_cast<const float2*>(E.rope)[(size_t)pos * (E.D >> 1) + (dd >> 1)];
-      o0 = __fsub_rn(__fmul_rn(a0, cs.x), __fmul_rn(a1, cs.y));
-      o1 = __fadd_rn(__fmul_rn(a1, cs.x), __fmul_rn(a0, cs.y));
+      o0 = __fsub_rn(__fmul_rn(a0, pre.cs.x), __fmul_rn(a1, pre.cs.y));
+      o1 = __fadd_rn(__fmul_rn(a1, pre.cs.x), __fmul_rn(a0, pre.cs.y));
     }
     __nv_bfloat16* dst;
     if (sec == 0) dst = static_cast<__nv_bfloat16*>(E.q_out) + (size_t)r * E.dim + cc;
@@ -194,101 +205,146 @@ __device__ __forceinline__ void gv_finish(const GvParams& P, int n, const float 
   }
 }
 
-// one GEMV phase with K = dim: the warps of the grid take the column pairs round-robin against the rows in `a`; `first` holds
-// this warp's first pair, requested before the barrier in front of the phase (weights do not depend on it)
-template <int MODE, int R, int ND>
-__device__ __forceinline__ void gv_phase(const GvParams& P, const __nv_bfloat16* W, int N, const uint4 (&a)[R][ND],
-                                         const GvPair<ND>& first, int gw, int tw, int lane) {
-  const int K = P.dim;
-  GvPair<ND> cur = first;
-  for (int n = 2 * gw; n < N; n += 2 * tw) {
-    GvPair<ND> nxt;
-    const int n2 = n + 2 * tw;
-    if (n2 < N) gv_load_pair<ND>(W, K, n2, lane, nxt);
-    float acc[R][2];
+// One GEMV phase of a consumer warp: the stages of this CTA's block of pairs arrive in order; stage number gs (counted over
+// the whole launch, in step with the producer) belongs to warp gs % kGvWarps.  Up to kGP pairs of a stage are multiplied
+// together (4 * kGP independent accumulation chains, the activation chunk unpacked once for all of them) against the rows
+// in shared memory.
+constexpr int kGP = 3;
+template <int MODE, int R>
+__device__ __forceinline__ void gv_phase(const GvParams& P, int N, int K, const uint8_t* acts, int pos, uint32_t& gs, uint8_t* ring, GvSmem& sm,
+                                         int warp, int lane) {
+  int p0, p1;
+  gv_range(N >> 1, p0, p1);
+  const int pps = gv_pairs_per_stage(K), per_row = K >> 3;
+  for (int p = p0; p < p1; p += pps, ++gs) {
+    if ((int)(gs % kGvWarps) != warp) continue;
+    const uint32_t st = gs % kGvStages, it = gs / kGvStages;
+    const int np = min(pps, p1 - p);
+    bool waited = false;
+#pragma unroll 1
+    for (int q0 = 0; q0 < np; q0 += kGP) {
+      const int g = min(kGP, np - q0);
+      GvPre pre[kGP];
 #pragma unroll
-    for (int r = 0; r < R; ++r) acc[r][0] = acc[r][1] = 0.f;
-    gv_dot_accum<R, ND>(cur, a, K, acc);
-    gv_reduce<R>(acc);
-    gv_finish<MODE, R>(P, n, acc, lane);
-    if (n2 < N) cur = nxt;
-  }
-}
-
-// w2 (K = hidden, up to 22 chunks per lane): a pair's rows and the activation rows pass through the registers in segments of
-// ND chunks; `first` holds segment 0 of this warp's first pair
-template <int R, int ND>
-__device__ __forceinline__ void gv_phase_w2(const GvParams& P, const GvPair<ND>& first, int gw, int tw, int lane) {
-  const int K = P.hidden, nch = K >> 8;
-  for (int n = 2 * gw; n < P.dim; n += 2 * tw) {
-    float acc[R][2];
+      for (int j = 0; j < kGP; ++j)
+        if (j < g) pre[j] = gv_prefetch<MODE>(P, 2 * (p + q0 + j), pos, lane);
+      if (!waited) { mbar_wait(&sm.full[st], it & 1); waited = true; }
+      const uint8_t* wbase = ring + st * kGvStageBytes + (size_t)q0 * 4 * K;
+      float acc[kGP][R][2];
 #pragma unroll
-    for (int r = 0; r < R; ++r) acc[r][0] = acc[r][1] = 0.f;
-    for (int c0 = 0; c0 < nch; c0 += ND) {
-      GvPair<ND> wseg;
-      if (c0 == 0 && n == 2 * gw) wseg = first;
-      else gv_load_pair<ND>(P.w2, K, n, lane, wseg, c0);
-      uint4 a[R][ND];
-      gv_load_rows<R, ND>(P.ffn, K, P.rows, lane, a, c0);
-      gv_dot_accum<R, ND>(wseg, a, K, acc, c0);
+      for (int j = 0; j < kGP; ++j)
+#pragma unroll
+        for (int r = 0; r < R; ++r) acc[j][r][0] = acc[j][r][1] = 0.f;
+#pragma unroll 1
+      for (int c = lane; c < per_row; c += 32) {
+        float f[R][8];
+#pragma unroll
+        for (int r = 0; r < R; ++r) gv_unpack(gv_lds128(acts + (size_t)r * 2 * K + c * 16), f[r]);
+#pragma unroll
+        for (int j = 0; j < kGP; ++j) {
+          if (j >= g) continue;
+          float w0[8], w1[8];
+          gv_unpack(gv_lds128(wbase + (size_t)j * 4 * K + c * 16), w0);
+          gv_unpack(gv_lds128(wbase + (size_t)j * 4 * K + 2 * K + c * 16), w1);
+#pragma unroll
+          for (int r = 0; r < R; ++r)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              acc[j][r][0] = fmaf(f[r][i], w0[i], acc[j][r][0]);
+              acc[j][r][1] = fmaf(f[r][i], w1[i], acc[j][r][1]);
+            }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < kGP; ++j)
+        if (j < g) gv_reduce<R>(acc[j]);
+#pragma unroll
+      for (int j = 0; j < kGP; ++j)
+        if (j < g) gv_finish<MODE, R>(P, 2 * (p + q0 + j), pos, pre[j], acc[j], lane);
     }
-    gv_reduce<R>(acc);
-    gv_finish<GV_RESID, R>(P, n, acc, lane);
+    __syncwarp();                                     // every lane is done reading the stage
+    if (lane == 0) mbar_arrive(&sm.empty[st]);
   }
 }
 
-template <int R, int ND>
+// producer: this CTA's block of pairs of one matrix, one bulk copy per stage (the rows of consecutive pairs are contiguous)
+__device__ __forceinline__ void gv_stream(const __nv_bfloat16* W, int N, int K, uint32_t& gs, uint8_t* ring, GvSmem& sm) {
+  int p0, p1;
+  gv_range(N >> 1, p0, p1);
+  const int pps = gv_pairs_per_stage(K);
+  for (int p = p0; p < p1; p += pps, ++gs) {
+    const uint32_t st = gs % kGvStages, it = gs / kGvStages;
+    const uint32_t bytes = (uint32_t)min(pps, p1 - p) * 4u * (uint32_t)K;
+    mbar_wait(&sm.empty[st], (it & 1) ^ 1);
+    mbar_expect_tx(&sm.full[st], bytes);
+    gv_bulk_g2s(ring + st * kGvStageBytes, W + (size_t)2 * p * K, bytes, &sm.full[st]);
+  }
+}
+
+template <int R>
 __global__ void __launch_bounds__(kGvThreads, 1) layer_tail_gemv_kernel(const __grid_constant__ GvParams P) {
+  extern __shared__ uint8_t gv_smem_raw[];
+  uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(gv_smem_raw) + 127) & ~uintptr_t(127));
+  uint8_t* acts = ring + kGvStages * kGvStageBytes;
+  GvSmem& sm = *reinterpret_cast<GvSmem*>(acts + kGvActBytes);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int gw = blockIdx.x * kGvWarps + warp, tw = gridDim.x * kGvWarps;
   const int d = P.dim, hid = P.hidden;
-  unsigned bar_target = 0;
-  pdl_launch_dependents();
-  // the first phase's weights do not depend on the previous kernel
-  GvPair<ND> fd;
-  if (P.has_front) { if (2 * gw < d) gv_load_pair<ND>(P.wo, d, 2 * gw, lane, fd); }
-  else if (2 * gw < 3 * d) gv_load_pair<ND>(P.wqkv, d, 2 * gw, lane, fd);
-  pdl_wait();
-
-  if (P.has_front) {
-    {
-      uint4 a[R][ND];
-      gv_load_rows<R, ND>(P.attn, d, P.rows, lane, a);
-      gv_phase<GV_RESID, R, ND>(P, P.wo, d, a, fd, gw, tw, lane);
-    }
-    if (2 * gw < 2 * hid) gv_load_pair<ND>(P.w13, d, 2 * gw, lane, fd);
-    gv_grid_barrier(P.bar, bar_target, P.err);
-    {
-      uint4 a[R][ND];
-      gv_load_rows<R, ND>(P.h, d, P.rows, lane, a);
-      gv_norm_rows<R, ND>(P.norm1_w, d, P.eps, lane, a);
-      gv_phase<GV_SWIGLU, R, ND>(P, P.w13, 2 * hid, a, fd, gw, tw, lane);
-    }
-    if (2 * gw < d) gv_load_pair<ND>(P.w2, hid, 2 * gw, lane, fd);
-    gv_grid_barrier(P.bar, bar_target, P.err);
-    gv_phase_w2<R, ND>(P, fd, gw, tw, lane);
-    if (P.has_qkv && 2 * gw < 3 * d) gv_load_pair<ND>(P.wqkv, d, 2 * gw, lane, fd);
-    gv_grid_barrier(P.bar, bar_target, P.err);
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kGvStages; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], 1); }
+    fence_mbar_init();
   }
+  __syncthreads();
+  pdl_launch_dependents();
+  uint32_t gs = 0;
+  if (warp == kGvWarps) {
+    // ---- producer: the weights depend on nothing -- neither on the previous kernel nor on this kernel's barriers
+    if (elect_one()) {
+      if (P.has_front) {
+        gv_stream(P.wo, d, d, gs, ring, sm);
+        gv_stream(P.w13, 2 * hid, d, gs, ring, sm);
+        gv_stream(P.w2, d, hid, gs, ring, sm);
+      }
+      if (P.has_qkv) gv_stream(P.wqkv, 3 * d, d, gs, ring, sm);
+    }
+    return;
+  }
+  // ---- consumers
+  unsigned bar_target = 0;
+  GV_TS(0);
+  pdl_wait();
+  GV_TS(1);
+  if (P.has_front) {
+    gv_stage_rows<R>(P.attn, d, P.rows, nullptr, 0.f, acts, warp, lane);
+    gv_phase<GV_RESID, R>(P, d, d, acts, 0, gs, ring, sm, warp, lane);
+    GV_TS(2);
+    gv_grid_barrier(P.bar, bar_target, P.err);
+    GV_TS(3);
+    gv_stage_rows<R>(P.h, d, P.rows, P.norm1_w, P.eps, acts, warp, lane);
+    GV_TS(4);
+    gv_phase<GV_SWIGLU, R>(P, 2 * hid, d, acts, 0, gs, ring, sm, warp, lane);
+    GV_TS(5);
+    gv_grid_barrier(P.bar, bar_target, P.err);
+    GV_TS(6);
+    gv_stage_rows<R>(P.ffn, hid, P.rows, nullptr, 0.f, acts, warp, lane);
+    GV_TS(7);
+    gv_phase<GV_RESID, R>(P, d, hid, acts, 0, gs, ring, sm, warp, lane);
+    GV_TS(8);
+    gv_grid_barrier(P.bar, bar_target, P.err);
+    GV_TS(9);
+  }
+  const int pos = P.has_qkv ? (P.rope.pos_ptr ? *P.rope.pos_ptr : P.rope.pos_imm) : 0;
+  gv_stage_rows<R>(P.h, d, P.rows, P.norm2_w, P.eps, acts, warp, lane);      // (behind a grid barrier, or first thing in the launch)
+  GV_TS(10);
   if (P.has_qkv) {
-    uint4 a[R][ND];
-    gv_load_rows<R, ND>(P.h, d, P.rows, lane, a);
-    gv_norm_rows<R, ND>(P.norm2_w, d, P.eps, lane, a);
-    gv_phase<GV_ROPE, R, ND>(P, P.wqkv, 3 * d, a, fd, gw, tw, lane);
-  } else if (gw == 0) {                                  // after the last layer: the head GEMM reads xn from global memory
-    uint4 a[R][ND];
-    gv_load_rows<R, ND>(P.h, d, P.rows, lane, a);
-    gv_norm_rows<R, ND>(P.norm2_w, d, P.eps, lane, a);
-    const int nch = d >> 8;
-#pragma unroll
-    for (int r = 0; r < R; ++r)
-#pragma unroll
-      for (int ch = 0; ch < ND; ++ch)
-        if (ch < nch && r < P.rows) *reinterpret_cast<uint4*>(P.xn + (size_t)r * d + (ch * 32 + lane) * 8) = a[r][ch];
+    gv_phase<GV_ROPE, R>(P, 3 * d, d, acts, pos, gs, ring, sm, warp, lane);
+    GV_TS(11);
+  } else if (blockIdx.x == 0) {                          // after the last layer: the head GEMM reads xn from global memory
+    for (int i = threadIdx.x; i < P.rows * (d >> 3); i += kGvWarps * 32)
+      *reinterpret_cast<uint4*>(P.xn + (size_t)i * 8) = *reinterpret_cast<const uint4*>(acts + (size_t)i * 16);
   }
 
   // leave the counters at zero for the next launch
-  __syncthreads();
+  asm volatile("bar.sync 1, %0;" ::"n"(kGvWarps * 32) : "memory");
   if (threadIdx.x == 0) {
     const unsigned old = atomicAdd(P.bar + 1, 1u);
     if (old == gridDim.x - 1) {
@@ -301,8 +357,8 @@ __global__ void __launch_bounds__(kGvThreads, 1) layer_tail_gemv_kernel(const __
 
 bool layer_tail_gemv_supported(int rows, int dim, int hidden) {
   static const bool off = [] { const char* e = getenv("VLG_LT_GEMV"); return e && e[0] == '0'; }();
-  return !off && rows >= 1 && rows <= kGvMaxRows && dim % 256 == 0 && hidden % 256 == 0 &&
-         (dim == 768 || dim == 1024 || dim == 1280 || dim == 1536);    // dim 2048 spills at 2 rows (255 registers): tensor-core tail
+  return !off && rows >= 1 && rows <= kGvMaxRows && dim % 256 == 0 && hidden % 256 == 0 && 4 * hidden <= kGvStageBytes && kGvMaxRows * 2 * hidden <= kGvActBytes &&
+         kGvMaxRows * 2 * dim <= kGvActBytes;
 }
 
 int launch_layer_tail_gemv(const LtLaunch& a, cudaStream_t st) {
@@ -322,15 +378,28 @@ int launch_layer_tail_gemv(const LtLaunch& a, cudaStream_t st) {
   P.rope = a.rope;
   P.bar = a.bar;
   P.err = a.err;
+  static const int dbg = [] { const char* e = getenv("VLG_LT_DEBUG"); return e ? atoi(e) : 0; }();
+  P.dbg = dbg;
   const dim3 grid(num_sms()), block(kGvThreads);
-#define VLG_GV_CASE(ND_)                                                                                 \
-  if (a.dim == ND_ * 256) {                                                                              \
-    if (a.rows == 1) VLG_CUDA(launch_kernel(layer_tail_gemv_kernel<1, ND_>, grid, block, 0, st, P));     \
-    else VLG_CUDA(launch_kernel(layer_tail_gemv_kernel<2, ND_>, grid, block, 0, st, P));                 \
+  const size_t smem = (size_t)kGvStages * kGvStageBytes + kGvActBytes + sizeof(GvSmem) + 128;
+  static PerDeviceOnce once1, once2;
+  if (a.rows == 1) {
+    auto kern = layer_tail_gemv_kernel<1>;
+    VLG_CUDA(once1([&] { return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); }));
+    VLG_CUDA(launch_kernel(kern, grid, block, smem, st, P));
+  } else {
+    auto kern = layer_tail_gemv_kernel<2>;
+    VLG_CUDA(once2([&] { return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); }));
+    VLG_CUDA(launch_kernel(kern, grid, block, smem, st, P));
   }
-  VLG_GV_CASE(3) VLG_GV_CASE(4) VLG_GV_CASE(5) VLG_GV_CASE(6)
-#undef VLG_GV_CASE
   VLG_LAUNCH_CHECK();
+  return VLG_OK;
+}
+
+// instrumentation: the stamps of the last full GEMV-tail launch (vlg_debug_lt_timestamps adds them behind the tensor-core
+// kernel's: out[160 * 32 ...])
+int layer_tail_gemv_timestamps(unsigned long long* out_host) {
+  VLG_CUDA(cudaMemcpyFromSymbol(out_host, g_gv_ts, sizeof(unsigned long long) * 160 * 32));
   return VLG_OK;
 }
 
