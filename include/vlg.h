@@ -316,9 +316,6 @@ int vlg_debug_gemm_timestamps(unsigned long long* out16_host);
 int vlg_debug_trunk_without_attention(vlg_ctx* ctx, int pos, void* stream);
 /* instrumentation (VLG_LT_DEBUG=1): globaltimer phase stamps [160 CTAs][32 slots] of the last full layer-tail launch */
 int vlg_debug_lt_timestamps(unsigned long long* out_host);
-/* the same for the 1-2 row GEMV layer tail: slots 0 start, 1 after griddepcontrol.wait, 2 wo done, 3 barrier, 4 norm done, 5 w1|w3 done,
- * 6 barrier, 7 activations staged, 8 w2 done, 9 barrier, 10 norm done, 11 wqkv done (warp 0 of every CTA) */
-int vlg_debug_gv_timestamps(unsigned long long* out_host);
 /* verification of the CTA-pair (tcgen05 cta_group::2) GEMM building block: out [rows, N] fp32 = x [rows, K] . w [N, K]^T, bf16
  * operands; rows <= 128, K % 64 == 0, bnp in {64, 128} the pair's column tile, N % bnp == 0 */
 int vlg_debug_pair_gemm(const void* x_dev, const void* w_dev, float* out_dev, int rows, int N, int K, int bnp, void* stream);

@@ -170,12 +170,11 @@ def test_gptl_cfg2_full_size_bf16():
                                             ("GPT-XL", 2, 48),    # 96 rows: CTA pairs with a ragged second half (32 live rows)
                                             ("GPT-XXL", 2, 64),   # 128 rows: CTA pairs at d = 1536 (24 k-blocks through 13 stages)
                                             ("GPT-B", 2, 80),     # 160 rows: beyond the layer-tail kernel, per-op kernels
-                                            # 2 rows (one sample with guidance): the GEMV layer tail (layer_tail_gemv.cu) at
-                                            # d = 768 / 1024 / 1280 / 1536, hidden 2048 / 2816 / 3584 / 4096
+                                            # 2 rows (one sample with guidance) at d = 768 / 1024 / 1280 / 1536
                                             ("GPT-B", 3, 1), ("GPT-L", 2, 1), ("GPT-XL", 2, 1), ("GPT-XXL", 2, 1)])
 def test_layer_tail_geometries_bf16(name, n_layer, B):
-    """The persistent layer-tail kernels (tensor-core: split-K tile shapes, ring wrap-around, row phases; 1-2 rows: column-pair
-    GEMVs) at the widths of the other registry entries -- d = 768 / 1280 / 1536 / 2048, hidden 2048 / 3584 / 4096 / 5632, 8..128 cache rows (single CTAs up to 64
+    """The persistent layer-tail kernel (split-K tile shapes, ring wrap-around, row phases) at the widths of the other
+    registry entries -- d = 768 / 1280 / 1536 / 2048, hidden 2048 / 3584 / 4096 / 5632, 8..128 cache rows (single CTAs up to 64
     rows, CTA pairs above) -- on a few layers: teacher-forced bf16 logits against the oracle on the same GPU."""
     kw = dict(O.NAMED[name])
     kw["n_layer"] = n_layer
@@ -440,9 +439,9 @@ def test_two_contexts_on_two_streams_do_not_share_the_layer_tail_kernel():
     assert n2 - n1 > n1 - n0, "the concurrent context must have fallen back to the per-op kernels"
 
 
-def test_single_sample_generate_loop_through_the_gemv_tail():
-    """One class label with guidance (2 cache rows, GPT-L width): the whole graph-replayed generate() loop through the GEMV
-    layer tail (per-step logits against the oracle are covered by test_layer_tail_geometries_bf16): determinism, token range,
+def test_single_sample_generate_loop():
+    """One class label with guidance (2 cache rows, GPT-L width): the whole graph-replayed generate() loop at the smallest
+    row count (per-step logits against the oracle are covered by test_layer_tail_geometries_bf16): determinism, token range,
     a one-row run without guidance, and the greedy loop against the oracle's greedy loop in bf16 on the same GPU."""
     torch.manual_seed(0)
     kw = dict(O.NAMED["GPT-L"])

@@ -1,5 +1,5 @@
 """The layer-tail launches of one decode position timed alone (attention skipped), per model and row count:
-    python tools/tail_alone.py GPT-XL 2        (VLG_LT_GEMV=0 for the tensor-core tail at 1-2 rows)"""
+    python tools/tail_alone.py GPT-XL 2"""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "video-llamagen_b200")]

@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "lib")
 LIB = os.path.join(OUT, "libvlg.so")
-UNITS = ["util.cu", "vq.cu", "elementwise.cu", "gemm.cu", "attn_generic.cu", "attn_tma.cu", "layer_tail.cu", "layer_tail_gemv.cu", "pair_gemm.cu", "sample.cu", "diff_head.cu", "api.cu"]
+UNITS = ["util.cu", "vq.cu", "elementwise.cu", "gemm.cu", "attn_generic.cu", "attn_tma.cu", "layer_tail.cu", "pair_gemm.cu", "sample.cu", "diff_head.cu", "api.cu"]
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
          "--use_fast_math=false", "-Xptxas", "-v"]
 

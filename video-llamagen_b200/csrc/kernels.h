@@ -71,12 +71,6 @@ struct LtLaunch {
 bool layer_tail_supported(int rows, int dim, int hidden);
 size_t layer_tail_scratch_bytes(int max_rows, int dim, int hidden);
 int launch_layer_tail(const LtLaunch& a, cudaStream_t st);
-// the same for 1-2 rows without tensor cores: column-pair GEMVs streamed from global memory, three grid barriers (layer_tail_gemv.cu);
-// launch_layer_tail dispatches to it
-bool layer_tail_gemv_supported(int rows, int dim, int hidden);
-int launch_layer_tail_gemv(const LtLaunch& a, cudaStream_t st);
-int layer_tail_gemv_timestamps(unsigned long long* out_host);   // [160][32] globaltimer stamps, VLG_LT_DEBUG=1
-
 // Fused CFG mix + temperature + top-k/top-p + softmax + pick.
 struct SampleArgs {
   const float* logits;  // [rows, V]

@@ -709,7 +709,6 @@ size_t layer_tail_scratch_bytes(int max_rows, int dim, int hidden) {
 int launch_layer_tail(const LtLaunch& a, cudaStream_t st) {
   VLG_REQUIRE(layer_tail_supported(a.rows, a.dim, a.hidden), "layer_tail: unsupported shape rows=%d dim=%d hidden=%d", a.rows, a.dim, a.hidden);
   VLG_REQUIRE(a.wo || a.wqkv, "layer_tail: nothing to do");
-  if (layer_tail_gemv_supported(a.rows, a.dim, a.hidden)) return launch_layer_tail_gemv(a, st);
   const int sms = num_sms();
   LtParams P{};
   P.rows = a.rows; P.dim = a.dim; P.hidden = a.hidden;
@@ -796,5 +795,3 @@ extern "C" int vlg_debug_lt_timestamps(unsigned long long* out_host) {
   VLG_CUDA(cudaMemcpyFromSymbol(out_host, vlg::g_lt_ts, sizeof(unsigned long long) * 160 * 32));
   return VLG_OK;
 }
-// the same for the 1-2 row GEMV tail (layer_tail_gemv.cu)
-extern "C" int vlg_debug_gv_timestamps(unsigned long long* out_host) { return vlg::layer_tail_gemv_timestamps(out_host); }

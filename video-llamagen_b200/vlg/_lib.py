@@ -88,7 +88,6 @@ SIGNATURES = {
     "vlg_debug_fp32_fma_peak": (_I, [_I, _I, _P, C.POINTER(C.c_longlong), _P]),
     "vlg_debug_gemm_timestamps": (_I, [_P]),
     "vlg_debug_lt_timestamps": (_I, [_P]),
-    "vlg_debug_gv_timestamps": (_I, [_P]),
     "vlg_debug_pair_gemm": (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),
     "vlg_debug_trunk_without_attention": (_I, [_P, _I, _P]),
 }
