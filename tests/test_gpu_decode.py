@@ -461,5 +461,8 @@ def test_single_sample_generate_loop():
     geo = O.Geometry(block_size=64, vocab_size=1024, **kw)
     g_ours = generate(m, cond, 24, cfg_scale=4.0, temperature=1.0, top_k=1, top_p=1.0, sample_logits=False)
     g_ref = O.generate(geo, w16, cond, 24, cfg_scale=4.0, temperature=1.0, top_k=1, top_p=1.0, sample_logits=False)
-    agree = (g_ours.cpu() == g_ref.cpu()).float().mean().item()
-    assert agree >= 0.5, agree            # chaotic after the first near-tie; a wrong kernel gives ~1/1024
+    # a greedy loop is chaotic after its first near-tie (two bf16 implementations differ by summation order), so only the head of
+    # the sequence is comparable token for token; a wrong kernel agrees with probability ~1/1024 per token
+    ours, ref = g_ours.cpu()[0], g_ref.cpu()[0]
+    assert torch.equal(ours[:4], ref[:4]), (ours[:8], ref[:8])
+    assert (ours == ref).float().mean().item() >= 0.1
