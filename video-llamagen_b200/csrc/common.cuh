@@ -166,11 +166,17 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug turns into a trap (reported as a CUDA error) instead of a hung GPU.
+// Bounded wait: a protocol bug turns into a trap (reported as a CUDA error) instead of a hung GPU.  The report is a real
+// function, not inlined: a printf call site is ~25 instructions, and the persistent kernels have dozens of waits whose code is
+// fetched cold on every launch.
+static __device__ __noinline__ void mbar_timeout() {
+  printf("vlg: mbarrier timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+  __trap();
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 26)) { printf("vlg: mbarrier timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x); __trap(); }
+    if (++spins > (1u << 26)) mbar_timeout();
   }
 }
 

@@ -86,12 +86,18 @@ struct LtParams {
 // phase timestamps (globaltimer ns) of every CTA of the last full (front + qkv) launch, VLG_LT_DEBUG=1: instrumentation
 // for tools/lt_phases.py.  Slots 0-15: thread 0 (producer / barrier view); 16-31: first TMEM-reader thread (accumulator view).
 __device__ unsigned long long g_lt_ts[160 * 32];
+// EXTRA (template parameter of the kernel and of lt_gemm_phase): the instrumented build of the kernel -- phase timestamps, the
+// optional L2 prefetch slices, the exact-SiLU switch.  The kernel the decode loop launches has none of it COMPILED IN: every
+// phase runs once per launch, so its instructions are fetched cold, and those three features were 115 of the kernel's 194 KB
+// of SASS (ncu: "no instruction" was the second-largest warp-state bucket).  79 KB: 778 -> 743 ms per cfg-2 generate.
 #define LT_TS_AT(i)                                                                                   \
   do {                                                                                                \
-    if (P.dbg && P.has_front && P.has_qkv && blockIdx.x < 160) {                                      \
-      unsigned long long t_;                                                                          \
-      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_));                                           \
-      g_lt_ts[blockIdx.x * 32 + (i)] = t_;                                                            \
+    if constexpr (EXTRA) {                                                                            \
+      if (P.dbg && P.has_front && P.has_qkv && blockIdx.x < 160) {                                    \
+        unsigned long long t_;                                                                        \
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_));                                         \
+        g_lt_ts[blockIdx.x * 32 + (i)] = t_;                                                          \
+      }                                                                                               \
     }                                                                                                 \
   } while (0)
 #define LT_TS(i) do { if (threadIdx.x == 0) LT_TS_AT(i); } while (0)
@@ -239,7 +245,7 @@ __device__ __forceinline__ void lt_prefetch_b(const LtGemm& G, const TensorMap* 
 
 // MODE: -1 = store the fp32 partial tile (split-K, reduced by the following row phase); EPI_SWIGLU / EPI_QKV_ROPE = the unit
 // owns all of K and applies the elementwise tail straight from TMEM (lane == row).
-template <int MODE, int ST, int SB, bool PAIR>
+template <int MODE, int ST, int SB, bool PAIR, bool EXTRA>
 __device__ __forceinline__ void lt_gemm_phase(const LtGemm& G, const TensorMap* tmA, const TensorMap* tmB,
                                               const LtGemm* Gnext, const TensorMap* tmBnext, const LtParams& P,
                                               const EpiParams& E, uint8_t* ring, LtSmem<ST>& sm, uint32_t tmem_acc, uint32_t& g, uint32_t& acc_uses,
@@ -366,7 +372,7 @@ __device__ __forceinline__ void lt_gemm_phase(const LtGemm& G, const TensorMap* 
             float o[16];
             // one branch around two straight-line loops: with the choice made per element ptxas keeps the 16 independent
             // MUFU chains in sequence (measured: 2.0 us for this block, most of the phase's epilogue)
-            if (P.fast_silu) {       // 2-3 ulp of fp32 before the bf16 rounding of silu (2^-9 relative)
+            if (!EXTRA || P.fast_silu) {       // 2-3 ulp of fp32 before the bf16 rounding of silu (2^-9 relative)
 #pragma unroll
               for (int i = 0; i < 16; i += 2) {
                 float a0 = v[2 * i], b0 = v[2 * i + 1], a1 = v[2 * i + 2], b1 = v[2 * i + 3];
@@ -480,7 +486,7 @@ __device__ __forceinline__ void lt_norm_phase(const LtGemm* G, const __nv_bfloat
 }
 
 // ---------------------------------------------------------------------------------------------------- the kernel
-template <int ST, int SB, bool PAIR>
+template <int ST, int SB, bool PAIR, bool EXTRA>
 __global__ void __launch_bounds__(kLtThreads, 1)
 layer_tail_kernel(const __grid_constant__ TensorMap tmAttn, const __grid_constant__ TensorMap tmXn,
                   const __grid_constant__ TensorMap tmFfn, const __grid_constant__ TensorMap tmWo,
@@ -524,41 +530,44 @@ layer_tail_kernel(const __grid_constant__ TensorMap tmAttn, const __grid_constan
   pdl_wait();
   LT_TS(1);
 
-  const int pf_slices = (P.has_front ? 5 : 1) + (P.has_qkv ? 1 : 0);
-  int pf_i = 0;
+  // (Measured: the phases as a loop over a small state machine -- wo / w2 and the two row phases sharing one copy of their code,
+  // one barrier call site; 77 -> 65 KB of SASS -- is slower, 847 against 743 ms: the operands picked at run time go through
+  // local memory.  Straight-line code it stays.)
+  [[maybe_unused]] const int pf_slices = (P.has_front ? 5 : 1) + (P.has_qkv ? 1 : 0);
+  [[maybe_unused]] int pf_i = 0;
   if (P.has_front) {
-    lt_pf_slice(P, pf_i++, pf_slices);
-    lt_gemm_phase<-1, ST, SB, PAIR>(P.g_wo, &tmAttn, &tmWo, &P.g_w13, &tmW13, P, P.ffn, ring, sm, tmem_acc, g, acc_uses, 16);
+    if constexpr (EXTRA) lt_pf_slice(P, pf_i++, pf_slices);
+    lt_gemm_phase<-1, ST, SB, PAIR, EXTRA>(P.g_wo, &tmAttn, &tmWo, &P.g_w13, &tmW13, P, P.ffn, ring, sm, tmem_acc, g, acc_uses, 16);
     LT_TS(2);
     lt_grid_barrier(P.bar, bar_target, P.err);
     LT_TS(3);
-    lt_pf_slice(P, pf_i++, pf_slices);
+    if constexpr (EXTRA) lt_pf_slice(P, pf_i++, pf_slices);
     lt_norm_phase(&P.g_wo, P.norm1_w, P, sm);
     LT_TS(4);
     lt_grid_barrier(P.bar, bar_target, P.err);
     LT_TS(5);
-    lt_pf_slice(P, pf_i++, pf_slices);
-    lt_gemm_phase<EPI_SWIGLU, ST, SB, PAIR>(P.g_w13, &tmXn, &tmW13, &P.g_w2, &tmW2, P, P.ffn, ring, sm, tmem_acc, g, acc_uses, 18);
+    if constexpr (EXTRA) lt_pf_slice(P, pf_i++, pf_slices);
+    lt_gemm_phase<EPI_SWIGLU, ST, SB, PAIR, EXTRA>(P.g_w13, &tmXn, &tmW13, &P.g_w2, &tmW2, P, P.ffn, ring, sm, tmem_acc, g, acc_uses, 18);
     LT_TS(6);
     lt_grid_barrier(P.bar, bar_target, P.err);
     LT_TS(7);
-    lt_pf_slice(P, pf_i++, pf_slices);
-    lt_gemm_phase<-1, ST, SB, PAIR>(P.g_w2, &tmFfn, &tmW2, P.has_qkv ? &P.g_qkv : nullptr, &tmWqkv, P, P.ffn, ring, sm, tmem_acc, g, acc_uses, 20);
+    if constexpr (EXTRA) lt_pf_slice(P, pf_i++, pf_slices);
+    lt_gemm_phase<-1, ST, SB, PAIR, EXTRA>(P.g_w2, &tmFfn, &tmW2, P.has_qkv ? &P.g_qkv : nullptr, &tmWqkv, P, P.ffn, ring, sm, tmem_acc, g, acc_uses, 20);
     LT_TS(8);
     lt_grid_barrier(P.bar, bar_target, P.err);
     LT_TS(9);
-    lt_pf_slice(P, pf_i++, pf_slices);
+    if constexpr (EXTRA) lt_pf_slice(P, pf_i++, pf_slices);
     lt_norm_phase(&P.g_w2, P.norm2_w, P, sm);
     LT_TS(10);
   } else {
-    lt_pf_slice(P, pf_i++, pf_slices);
+    if constexpr (EXTRA) lt_pf_slice(P, pf_i++, pf_slices);
     lt_norm_phase(nullptr, P.norm2_w, P, sm);
   }
   if (P.has_qkv) {
     lt_grid_barrier(P.bar, bar_target, P.err);
     LT_TS(11);
-    lt_pf_slice(P, pf_i++, pf_slices);
-    lt_gemm_phase<EPI_QKV_ROPE, ST, SB, PAIR>(P.g_qkv, &tmXn, &tmWqkv, nullptr, nullptr, P, P.rope, ring, sm, tmem_acc, g, acc_uses, 22);
+    if constexpr (EXTRA) lt_pf_slice(P, pf_i++, pf_slices);
+    lt_gemm_phase<EPI_QKV_ROPE, ST, SB, PAIR, EXTRA>(P.g_qkv, &tmXn, &tmWqkv, nullptr, nullptr, P, P.rope, ring, sm, tmem_acc, g, acc_uses, 22);
     LT_TS(12);
   }
 
@@ -649,7 +658,7 @@ static bool lt_pairs_fit(int sms) {
   static int cached[kMaxDevices] = {};                      // 0 unknown, 1 yes, -1 no
   int& c = cached[current_device()];
   if (c == 0) {
-    auto kern = layer_tail_kernel<kLtStagesPair, kLtStageBytesPair, true>;
+    auto kern = layer_tail_kernel<kLtStagesPair, kLtStageBytesPair, true, false>;
     const int smem = lt_smem_bytes(kLtStagesPair, kLtStageBytesPair);
     int n = 0;
     cudaLaunchConfig_t cfg{};
@@ -768,22 +777,29 @@ int launch_layer_tail(const LtLaunch& a, cudaStream_t st) {
   if (P.has_qkv)
     if ((rc = make_tmap_bf16_2d(&tmWqkv, a.wqkv, (uint64_t)3 * a.dim, (uint64_t)a.dim, (uint64_t)a.dim * 2, P.g_qkv.BN >> (pair ? 1 : 0), 64, true))) return rc;
 
-  if (pair) {
-    auto kern = layer_tail_kernel<kLtStagesPair, kLtStageBytesPair, true>;
-    const int smem = lt_smem_bytes(kLtStagesPair, kLtStageBytesPair);
-    static PerDeviceOnce attr_once_pair;
-    VLG_CUDA(attr_once_pair([&] { return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); }));
-    VLG_CUDA(launch_kernel_cluster(kern, dim3(sms), dim3(kLtThreads), (size_t)smem, st, 2, tmAttn, tmXn, tmFfn, tmWo, tmW13, tmW2, tmWqkv, P));
-    VLG_LAUNCH_CHECK();
-    return VLG_OK;
+  // the instrumented variant only when one of its features is asked for (see EXTRA above)
+  const bool extra = dbg != 0 || fast_silu == 0 || P.pf_budget > 0 || P.pf_flat != nullptr;
+  const bool narrow = P.g_wo.BN <= 64 && P.g_w13.BN <= 64 && P.g_w2.BN <= 64 && P.g_qkv.BN <= 64;   // ring layout by the widest column tile in use
+#define VLG_LT_LAUNCH(ST_, SB_, PAIR_, EXTRA_, CLUSTER_)                                                                          \
+  {                                                                                                                               \
+    auto kern = layer_tail_kernel<ST_, SB_, PAIR_, EXTRA_>;                                                                       \
+    const int smem = lt_smem_bytes(ST_, SB_);                                                                                     \
+    static PerDeviceOnce attr_once;                                                                                               \
+    VLG_CUDA(attr_once([&] { return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); }));           \
+    if (CLUSTER_ > 1) VLG_CUDA(launch_kernel_cluster(kern, dim3(sms), dim3(kLtThreads), (size_t)smem, st, CLUSTER_, tmAttn, tmXn, tmFfn, tmWo, tmW13, tmW2, tmWqkv, P)); \
+    else VLG_CUDA(launch_kernel(kern, dim3(sms), dim3(kLtThreads), (size_t)smem, st, tmAttn, tmXn, tmFfn, tmWo, tmW13, tmW2, tmWqkv, P)); \
   }
-  // ring layout by the widest column tile in use (see kLtStagesNarrow)
-  const bool narrow = P.g_wo.BN <= 64 && P.g_w13.BN <= 64 && P.g_w2.BN <= 64 && P.g_qkv.BN <= 64;
-  auto kern = narrow ? layer_tail_kernel<kLtStagesNarrow, kLtStageBytesNarrow, false> : layer_tail_kernel<kLtStages, kLtStageBytesWide, false>;
-  const int smem = narrow ? lt_smem_bytes(kLtStagesNarrow, kLtStageBytesNarrow) : lt_smem_bytes(kLtStages, kLtStageBytesWide);
-  static PerDeviceOnce attr_once[2];
-  VLG_CUDA(attr_once[narrow]([&] { return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); }));
-  VLG_CUDA(launch_kernel(kern, dim3(sms), dim3(kLtThreads), (size_t)smem, st, tmAttn, tmXn, tmFfn, tmWo, tmW13, tmW2, tmWqkv, P));
+  if (pair) {
+    if (extra) VLG_LT_LAUNCH(kLtStagesPair, kLtStageBytesPair, true, true, 2)
+    else VLG_LT_LAUNCH(kLtStagesPair, kLtStageBytesPair, true, false, 2)
+  } else if (narrow) {
+    if (extra) VLG_LT_LAUNCH(kLtStagesNarrow, kLtStageBytesNarrow, false, true, 1)
+    else VLG_LT_LAUNCH(kLtStagesNarrow, kLtStageBytesNarrow, false, false, 1)
+  } else {
+    if (extra) VLG_LT_LAUNCH(kLtStages, kLtStageBytesWide, false, true, 1)
+    else VLG_LT_LAUNCH(kLtStages, kLtStageBytesWide, false, false, 1)
+  }
+#undef VLG_LT_LAUNCH
   VLG_LAUNCH_CHECK();
   return VLG_OK;
 }
