@@ -114,6 +114,19 @@ __device__ unsigned long long g_lt_ts[160 * 32];
 constexpr int kLtWorkers = kLtThreads - 32;
 __device__ __forceinline__ void lt_workers_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kLtWorkers) : "memory"); }
 
+// the bounded-wait bookkeeping of a barrier poll loop, out of line (six barriers are inlined into the kernel)
+static __device__ __noinline__ bool lt_barrier_gave_up(unsigned long long& t0, volatile unsigned* err) {
+  unsigned long long now;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+  if (t0 == 0) t0 = now;
+  if (err != nullptr && *err != 0) return true;                       // somebody already gave up
+  if (now - t0 > 2000000000ull) {
+    if (err != nullptr) { *err = 1u; __threadfence_system(); }
+    return true;
+  }
+  return false;
+}
+
 __device__ __forceinline__ void lt_grid_barrier(unsigned* ctr, unsigned& target, volatile unsigned* err) {
   target += gridDim.x;
   tc_fence_before();
@@ -129,16 +142,7 @@ __device__ __forceinline__ void lt_grid_barrier(unsigned* ctr, unsigned& target,
       for (;;) {
         asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(ctr) : "memory");
         if (seen >= target) break;
-        if ((++spins & 1023u) == 0) {
-          unsigned long long now;
-          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-          if (t0 == 0) t0 = now;
-          if (err != nullptr && *err != 0) break;                       // somebody already gave up
-          if (now - t0 > 2000000000ull) {
-            if (err != nullptr) { *err = 1u; __threadfence_system(); }
-            break;
-          }
-        }
+        if ((++spins & 1023u) == 0 && lt_barrier_gave_up(t0, err)) break;
       }
     }
   }
@@ -599,7 +603,7 @@ bool lt_pick(int N, int K, int sms, bool split, LtGemm* out, int max_bn) {
   if (K % 64 != 0 || N % 64 != 0) return false;
   const int nkb = K / 64;
   // split count cap: the row phase that reduces the partials keeps 8 loads per thread in flight per L2 round trip
-  static const int max_s = [] { const char* e = getenv("VLG_LT_MAXS"); return e ? atoi(e) : 8; }();
+  static const int max_s = [] { const char* e = getenv("VLG_LT_MAXS"); const int v = e ? atoi(e) : kLtMaxSplits; return v < 1 ? 1 : v > kLtMaxSplits ? kLtMaxSplits : v; }();
   double best = 1e30;
   bool found = false;
   const int bns[3] = {32, 64, 128};
@@ -629,7 +633,7 @@ bool lt_pick(int N, int K, int sms, bool split, LtGemm* out, int max_bn) {
 static bool lt_pick_pair(int N, int K, int pairs, bool split, int min_bn, LtGemm* out) {
   if (K % 64 != 0) return false;
   const int nkb = K / 64;
-  static const int max_s = [] { const char* e = getenv("VLG_LT_MAXS"); return e ? atoi(e) : 8; }();
+  static const int max_s = [] { const char* e = getenv("VLG_LT_MAXS"); const int v = e ? atoi(e) : kLtMaxSplits; return v < 1 ? 1 : v > kLtMaxSplits ? kLtMaxSplits : v; }();
   double best = 1e30;
   bool found = false;
   for (int bn : {64, 128}) {

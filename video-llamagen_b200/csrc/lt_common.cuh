@@ -50,32 +50,21 @@ __device__ __forceinline__ uint4 ldg128_cg(const void* p) {
   return r;
 }
 
-// sum of the S partials of 8 consecutive columns, fixed order
+// sum of the S <= kLtMaxSplits partials of 8 consecutive columns, fixed order; all loads in flight before the first add
+constexpr int kLtMaxSplits = 8;
 __device__ __forceinline__ void lt_reduce8(const float* part, int S, size_t split_stride, size_t off, float* acc) {
-  constexpr int kChunk = 8;          // loads in flight per thread before the first dependent add
-  float t[kChunk][8];
+  float t[kLtMaxSplits][8];
 #pragma unroll
-  for (int j = 0; j < kChunk; ++j)
+  for (int j = 0; j < kLtMaxSplits; ++j)
     if (j < S) ldg256(part + (size_t)j * split_stride + off, t[j]);
 #pragma unroll
   for (int i = 0; i < 8; ++i) acc[i] = t[0][i];
 #pragma unroll
-  for (int j = 1; j < kChunk; ++j)
+  for (int j = 1; j < kLtMaxSplits; ++j)
     if (j < S) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) acc[i] = __fadd_rn(acc[i], t[j][i]);
     }
-  for (int s0 = kChunk; s0 < S; s0 += kChunk) {
-#pragma unroll
-    for (int j = 0; j < kChunk; ++j)
-      if (s0 + j < S) ldg256(part + (size_t)(s0 + j) * split_stride + off, t[j]);
-#pragma unroll
-    for (int j = 0; j < kChunk; ++j)
-      if (s0 + j < S) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) acc[i] = __fadd_rn(acc[i], t[j][i]);
-      }
-  }
 }
 
 // Tile shape and split count per GEMM (host): see layer_tail.cu.  max_bn caps the column tile.
