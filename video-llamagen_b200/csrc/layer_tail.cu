@@ -535,8 +535,10 @@ layer_tail_kernel(const __grid_constant__ TensorMap tmAttn, const __grid_constan
   LT_TS(1);
 
   // (Measured: the phases as a loop over a small state machine -- wo / w2 and the two row phases sharing one copy of their code,
-  // one barrier call site; 77 -> 65 KB of SASS -- is slower, 847 against 743 ms: the operands picked at run time go through
-  // local memory.  Straight-line code it stays.)
+  // one barrier call site; 77 -> 65 KB of SASS -- is slower, 847 against 743 ms: operands picked by reference at run time move
+  // the parameter block to local memory.  With the operands copied by value (a two-trip loop around wo / w2, 59 KB, no stack
+  // frame) it is exactly as fast as this straight-line code, 740.8 against 740.3 ms: below ~77 KB the code size no longer
+  // matters.  Straight-line code it stays.)
   [[maybe_unused]] const int pf_slices = (P.has_front ? 5 : 1) + (P.has_qkv ? 1 : 0);
   [[maybe_unused]] int pf_i = 0;
   if (P.has_front) {
