@@ -299,16 +299,20 @@ vq_score_kernel(const float* __restrict__ z, const float* __restrict__ en, const
   }
 }
 
-// One warp per ambiguous latent: the reference's rounding sequence for d over all codes (same arithmetic as
-// vq_argmin_kernel), lanes stride the codebook, minimum with the lowest index on ties.
+// One CTA per ambiguous latent: the reference's rounding sequence for d over all codes (same arithmetic as
+// vq_argmin_kernel), the 256 threads stride the codebook (each scans its codes in increasing order, strict '<': first index
+// on ties), minimum with the lowest index on ties across the block.  (One WARP per latent, the first version, left ~300 of
+// 2368 warps busy for 512 dependent iterations each: 281 us, 4 % of the whole index search.)
 template <int C>
 __global__ void __launch_bounds__(256)
 vq_recheck_kernel(const float* __restrict__ z, const float* __restrict__ en, const float* __restrict__ e2,
                   int64_t* __restrict__ idx_out, float* __restrict__ zq, const unsigned* __restrict__ amb_count,
                   const int* __restrict__ amb_list, int64_t HW, int n_e, int l2_norm) {
-  const int lane = threadIdx.x & 31;
+  __shared__ float s_best[8];
+  __shared__ int s_bi[8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const unsigned total = *amb_count;
-  for (unsigned w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); w < total; w += gridDim.x * (blockDim.x >> 5)) {
+  for (unsigned w = blockIdx.x; w < total; w += gridDim.x) {
     const int64_t n = amb_list[w];
     const int64_t b = n / HW, hw = n % HW;
     float zr[C];
@@ -329,10 +333,22 @@ vq_recheck_kernel(const float* __restrict__ z, const float* __restrict__ en, con
     }
     float best = INFINITY;
     int bi = 0x7fffffff;
-    for (int j = lane; j < n_e; j += 32) {
-      float dot = __fmul_rn(zr[0], en[(size_t)j * C]);
+#pragma unroll 4
+    for (int j = threadIdx.x; j < n_e; j += 256) {
+      float e[C];
+      if constexpr (C % 4 == 0) {
 #pragma unroll
-      for (int c = 1; c < C; ++c) dot = __fmaf_rn(zr[c], en[(size_t)j * C + c], dot);
+        for (int c = 0; c < C; c += 4) {
+          const float4 v = __ldg(reinterpret_cast<const float4*>(en + (size_t)j * C + c));
+          e[c] = v.x; e[c + 1] = v.y; e[c + 2] = v.z; e[c + 3] = v.w;
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < C; ++c) e[c] = en[(size_t)j * C + c];
+      }
+      float dot = __fmul_rn(zr[0], e[0]);
+#pragma unroll
+      for (int c = 1; c < C; ++c) dot = __fmaf_rn(zr[c], e[c], dot);
       const float d = __fmaf_rn(-2.f, dot, __fadd_rn(ss, e2[j]));
       if (d < best) { best = d; bi = j; }
     }
@@ -342,6 +358,18 @@ vq_recheck_kernel(const float* __restrict__ z, const float* __restrict__ en, con
       const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
       if (ob < best || (ob == best && oi < bi)) { best = ob; bi = oi; }
     }
+    __syncthreads();                         // the previous item's readers of s_best / s_bi are done
+    if (lane == 0) { s_best[warp] = best; s_bi[warp] = bi; }
+    __syncthreads();
+    best = s_best[0];
+    bi = s_bi[0];
+#pragma unroll
+    for (int k = 1; k < 8; ++k) {
+      const float ob = s_best[k];
+      const int oi = s_bi[k];
+      if (ob < best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+    }
+    if (threadIdx.x >= 32) continue;         // warp 0 writes the result
     if (bi == 0x7fffffff) bi = 0;            // all-NaN row: torch.argmin would return the first NaN; index 0 here
     if (lane == 0) idx_out[n] = bi;
     if (zq && lane < C) zq[(b * C + lane) * HW + hw] = __fadd_rn(zr[lane], __fsub_rn(en[(size_t)bi * C + lane], zr[lane]));
@@ -561,7 +589,7 @@ static int launch_vq_fast(const float* z, const float* cb, int64_t* idx, float* 
     default: rc = launch(vq_score_kernel<4, 4>, 4); break;   // 6.52 ms / 1M latents ((4, 8): 6.55, spills at the 168-register cap; split chains: 6.8)
   }
   if (rc) return rc;
-  vq_recheck_kernel<C><<<num_sms() * 2, 256, 0, st>>>(z, en, e2, idx, zq, amb_count, amb_list, HW, n_e, l2_norm);
+  vq_recheck_kernel<C><<<num_sms() * 4, 256, 0, st>>>(z, en, e2, idx, zq, amb_count, amb_list, HW, n_e, l2_norm);
   VLG_LAUNCH_CHECK();
   return VLG_OK;
 }
