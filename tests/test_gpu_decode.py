@@ -95,6 +95,15 @@ def test_t2i_tiny_masked_prefix_fp32(golden):
         x = torch.cat([toks[:, i:i + 1], toks[:, i:i + 1]])
         out.append(m(x, None, torch.tensor([T + i], device=DEV))[0][:, -1])
     assert np.abs(torch.stack(out).cpu().numpy() - f["logits"]).max() < 1e-4
+    # the same prefix in ONE pass (vlg_forward_prefix): last-position logits against the reference fixture, and the K/V it left
+    # in the caches through the next position's logits
+    m.setup_caches(R, T + N, None)
+    m.set_prefix_mask(torch.cat([masks, masks]))
+    eng = m._engine
+    logits0 = eng.forward_prefix(eng.mlp(0, rows, 128)[:, :T], want_logits=True, want_hidden=False)[0]
+    assert np.abs(logits0.cpu().numpy() - f["logits"][0]).max() < 1e-4
+    x = torch.cat([toks[:, 0:1], toks[:, 0:1]])
+    assert np.abs(m(x, None, torch.tensor([T], device=DEV))[0][:, -1].cpu().numpy() - f["logits"][1]).max() < 1e-4
 
 
 def test_c2i_tiny_bf16_logits_within_tolerance(golden):
