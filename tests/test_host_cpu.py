@@ -100,6 +100,24 @@ def test_sample_script_import_lines_resolve_to_the_drop_ins():
         assert callable(getattr(vq, name))
 
 
+def test_diffusion_sampler_import_lines_resolve_to_the_drop_ins():
+    """The import lines of the fork's diffusion-head sampler that belong to the path (autoregressive/sample/
+    sample_t2v_1f_diff.py:28-29; gpt_video_diff.py:27 imports DiffLoss from a bare `diffloss` module in its own directory)."""
+    from autoregressive.models.generate_video_diff import generate
+    from autoregressive.models.gpt_video_diff import GPT_models
+    from autoregressive.models.diffloss import DiffLoss
+    import vlg.generate_video_diff, vlg.gpt_video_diff, vlg.diffloss
+    assert generate is vlg.generate_video_diff.generate and GPT_models is vlg.gpt_video_diff.GPT_models
+    assert DiffLoss is vlg.diffloss.DiffLoss and set(GPT_models) >= {"GPT-B", "GPT-L", "GPT-XL", "GPT-1B"}
+    # ctor kwargs of sample_t2v_1f_diff.py:86-97 on a small registry-shaped model
+    from vlg.gpt_video_diff import Transformer, ModelArgs
+    m = Transformer(ModelArgs(dim=128, n_layer=1, n_head=2, block_size=16, cls_token_num=120, caption_dim=32, vae_embed_dim=8,
+                              num_frames=1, model_type="t2v", vocab_size=64, diffloss_w=128, multiple_of=64))
+    assert m.model_type == "t2v" and m.diffloss.in_channels == 8 and m.seq_len == 16
+    with pytest.raises(NotImplementedError):
+        generate(m, torch.zeros(1, 120, 32), 4, cfg_scale=4.0)             # the reference's broken branch is refused, not invented
+
+
 def test_vqmodel_same_seed_same_weights_and_cnn_parity(golden):
     """VQ_models['VQ-16'] consumes torch's RNG like the reference's constructor (same keys, same weights per seed), and
     its encoder / decoder CNNs (library convolutions) reproduce the reference module's outputs on CPU fp32."""
