@@ -1,5 +1,8 @@
+"""One fp32 trunk position of the GPT-1B t2v model at batch 1 between cudaProfilerStart/Stop (the other half of a
+generate_video_diff token), for `ncu --profile-from-start off`:
+    ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file out.csv python tools/trunk_prof_fp32.py"""
 import os, sys, torch
-ROOT = "/root/repo"
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "video-llamagen_b200")]
 from vlg.gpt_video_diff import GPT_models
 torch.manual_seed(0)
