@@ -8,13 +8,13 @@
 // What the chain looks like once the parts that do not depend on the diffusing sample are taken out of it:
 //   * the conditioning c = cond_embed(z) is fixed for the token, the timestep embedding is fixed for the model, so every
 //     adaLN modulation  Linear(SiLU(t_emb[s] + c[r]))  of every step is known before the chain starts: ONE fp32 GEMM
-//     [steps*rows, W] x [W, (3*depth+2) W] per token (dh_precompute: gemm_f32_kernel) replaces depth+1 of the dependent
+//     [steps*rows, W] x [W, (3*depth+2) W] per token (dh_sgemm_kernel, CUDA-core fp32) replaces depth+1 of the dependent
 //     layers of every step and takes 2/3 of the weights out of the loop;
 //   * what is left per step is a dependent chain of 2*depth [W x W] layers and the [2C x W] output layer on `rows` vectors:
 //     no arithmetic to speak of (6 MFLOP per row), only latency.  dh_sample_kernel keeps those weights RESIDENT IN SHARED
 //     MEMORY for the whole chain -- 2*depth*W*W*4 B = 25 MB at W = 1024, depth = 3, spread over 128 CTAs x 192 KB, 8
 //     output columns each -- so that a layer is: read the [rows x W] activation from L2, LayerNorm + modulate in
-//     registers (every warp holds the rows it needs, lane-strided), eight warp-wide dot products against shared memory,
+//     registers (one row per warp at a time, lane-strided), warp-wide dot products against shared memory,
 //     store 8 columns, grid barrier.  2*depth + 1 barriers per diffusion step, nothing else leaves the SM; the posterior
 //     update is done redundantly by every CTA from the same [rows x 2C] output (deterministic: same inputs, same code).
 // One cooperative launch per token (the driver guarantees the grid is co-resident, which the barriers need).
